@@ -1,0 +1,119 @@
+/*
+ * tcb200.h — C ABI of the B200-native BLS12-381 threshold-crypto engine (libtcb200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of poanetwork/threshold_crypto
+ * (SURVEY.md §8): every entry point is the batched form of a reference method and is what
+ * a Rust `extern "C"` block in a patched `threshold_crypto` (or a shim crate) would bind —
+ * see INTEGRATION.md for the Rust-side declarations.  Citations are file:line under
+ * /root/reference.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; the caller owns every buffer; the library keeps
+ *     nothing after a call returns.  One tcb_ctx per calling thread (calls on one ctx are
+ *     serialised).  There is NO CPU fallback: without a CUDA device tcb_init fails.
+ *   - Return value: 0 = ok, < 0 = CUDA / argument failure (text via tcb_last_error).
+ *     Per-item scheme outcomes go to status[]: 0 ok, 1 NotEnoughShares (normally caught
+ *     by the caller, src/lib.rs:731-733), 2 DuplicateEntry (src/lib.rs:763; unreachable in
+ *     the reference because of its by-value filter, kept for ABI completeness),
+ *     3 invalid encoding (field element >= modulus).
+ *   - G1 points: EXTERNAL pairing 0.16 *uncompressed* affine encoding, 96 B = x || y
+ *     big-endian; G2 points: 192 B = x.c1 || x.c0 || y.c1 || y.c0; infinity = byte 0 bit
+ *     0x40 set, everything else zero (src/lib.rs:89,238-240 use the same encoding).
+ *     Points must be valid group elements (the Rust types guarantee it).
+ *   - Scalars (Fr): canonical (non-Montgomery) 4 x u64 little-endian = 32 B, the bytes
+ *     SerdeSecret / FieldWrap emit (src/serde_impl.rs:109,296).
+ *   - Messages: one concatenated byte buffer + (n+1) u64 offsets.
+ *   - `_dev` variants take DEVICE pointers (on ctx's first device) and a cudaStream_t
+ *     passed as void*; they only enqueue work.  They exist so that a caller that already
+ *     holds its batch in HBM (and bench.py's kernel-only timing) skips the copies.
+ */
+#ifndef TCB200_H
+#define TCB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tcb_ctx tcb_ctx;
+
+/* Engine variants for the G2 / pairing kernels (tcb_set_engine): */
+#define TCB_ENGINE_PAIR 0   /* one item per lane pair, Fp2 sliced across the pair (default) */
+#define TCB_ENGINE_THREAD 1 /* one item per thread */
+
+int tcb_init(tcb_ctx **ctx, const int *device_ids, int n_devices);
+void tcb_free(tcb_ctx *ctx);
+const char *tcb_last_error(const tcb_ctx *ctx);
+int tcb_set_engine(tcb_ctx *ctx, int engine);
+/* number of kernel launches issued through ctx since tcb_init (bench.py's gpu_launches) */
+uint64_t tcb_launch_count(const tcb_ctx *ctx);
+
+/* e(a,b) == e(c,d).  PublicKey::verify_g2 (src/lib.rs:108-110) with (a,b,c,d) =
+ * (pk, hash, g1, sig); PublicKeyShare::verify_decryption_share (:182-186) with
+ * (share, H(U,V), pk_i, W); Ciphertext::verify (:508-512) with (g1, W, U, H(U,V)).
+ * c_g1 == NULL means the G1 generator for every item. */
+int tcb_verify_g2_batch(tcb_ctx *, size_t n, const uint8_t *a_g1, const uint8_t *b_g2,
+                        const uint8_t *c_g1, const uint8_t *d_g2, uint8_t *ok);
+/* hash_g2 (src/lib.rs:691-694) */
+int tcb_hash_g2_batch(tcb_ctx *, size_t n, const uint8_t *msgs, const uint64_t *off, uint8_t *out_g2);
+/* PublicKey::verify / PublicKeyShare::verify (src/lib.rs:115-117,177-179) */
+int tcb_verify_batch(tcb_ctx *, size_t n, const uint8_t *pk_g1, const uint8_t *sig_g2,
+                     const uint8_t *msgs, const uint64_t *off, uint8_t *ok);
+/* SecretKey::sign / SecretKeyShare::sign (src/lib.rs:379-381,447-449) */
+int tcb_sign_batch(tcb_ctx *, size_t n, const uint8_t *sk, const uint8_t *msgs, const uint64_t *off,
+                   uint8_t *out_g2);
+/* SecretKey::sign_g2 (src/lib.rs:372-374) */
+int tcb_sign_g2_batch(tcb_ctx *, size_t n, const uint8_t *sk, const uint8_t *h_g2, uint8_t *out_g2);
+/* interpolate::<G2> behind PublicKeySet::combine_signatures (src/lib.rs:608-615,719-767).
+ * x_fr: n*(t+1) scalars, already i+1 (into_fr_plus_1, :769-773); shares: n*(t+1) G2. */
+int tcb_combine_g2_batch(tcb_ctx *, size_t n, size_t t, const uint8_t *x_fr, const uint8_t *shares_g2,
+                         uint8_t *out_g2, uint8_t *status);
+/* interpolate::<G1> (decryption shares) */
+int tcb_combine_g1_batch(tcb_ctx *, size_t n, size_t t, const uint8_t *x_fr, const uint8_t *shares_g1,
+                         uint8_t *out_g1, uint8_t *status);
+/* SecretKeyShare::decrypt_share_no_verify (src/lib.rs:460-462): out = sk_i * U_i */
+int tcb_decrypt_share_batch(tcb_ctx *, size_t n, const uint8_t *sk, const uint8_t *u_g1, uint8_t *out_g1);
+/* PublicKeySet::decrypt (src/lib.rs:618-626): interpolate::<G1> then xor_with_hash (:710-715) */
+int tcb_decrypt_batch(tcb_ctx *, size_t n, size_t t, const uint8_t *x_fr, const uint8_t *shares_g1,
+                      const uint8_t *v, const uint64_t *v_off, uint8_t *out, uint8_t *status);
+/* Commitment::evaluate (src/poly.rs:497-508) at n points of one commitment of degree deg */
+int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const uint8_t *coeff_g1, size_t n,
+                              const uint8_t *x_fr, uint8_t *out_g1);
+/* SecretKey::public_key / Poly::commitment (src/lib.rs:367-369, src/poly.rs:372-377): g1 * c */
+int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const uint8_t *sk, uint8_t *out_g1);
+
+/* Device-resident variants (inputs/outputs in HBM of ctx's first device; enqueue only). */
+int tcb_verify_g2_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *a_g1, const uint8_t *b_g2,
+                            const uint8_t *c_g1, const uint8_t *d_g2, uint8_t *ok);
+int tcb_hash_g2_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *msgs, const uint64_t *off,
+                          uint8_t *out_g2);
+int tcb_verify_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *pk_g1, const uint8_t *sig_g2,
+                         const uint8_t *msgs, const uint64_t *off, uint8_t *ok);
+int tcb_sign_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *sk, const uint8_t *msgs,
+                       const uint64_t *off, const uint8_t *h_g2, uint8_t *out_g2);
+int tcb_combine_g2_batch_dev(tcb_ctx *, void *stream, size_t n, size_t t, const uint8_t *x_fr,
+                             const uint8_t *shares_g2, uint8_t *out_g2, uint8_t *status);
+int tcb_combine_g1_batch_dev(tcb_ctx *, void *stream, size_t n, size_t t, const uint8_t *x_fr,
+                             const uint8_t *shares_g1, uint8_t *out_g1, uint8_t *status);
+int tcb_decrypt_batch_dev(tcb_ctx *, void *stream, size_t n, size_t t, const uint8_t *x_fr,
+                          const uint8_t *shares_g1, const uint8_t *v, const uint64_t *v_off,
+                          uint64_t v_total, uint8_t *out, uint8_t *status);
+int tcb_g1_mul_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *sk, const uint8_t *pts_g1 /*NULL = generator*/,
+                         uint8_t *out_g1);
+int tcb_commitment_eval_batch_dev(tcb_ctx *, void *stream, size_t deg, const uint8_t *coeff_g1, size_t n,
+                                  const uint8_t *x_fr, uint8_t *out_g1);
+
+/* Self-test / measurement helpers (used by tests and bench.py, not part of the drop-in surface). */
+/* Runs the PTX Montgomery multiply, dot2, add, sub against the portable CIOS on n random
+ * pairs on the device; returns the number of mismatches (0 = pass) or < 0 on CUDA failure. */
+int tcb_selftest_fp(tcb_ctx *, size_t n, uint64_t seed);
+/* Integer-MAC roofline probe: dependent-free IMAD.WIDE.U32 chains on every SM; writes the
+ * achieved 32x32->64 multiply-accumulates per second. */
+int tcb_probe_imad(tcb_ctx *, double *macs_per_sec);
+/* Fp multiplication throughput (independent chains, all SMs): Montgomery muls per second. */
+int tcb_probe_fpmul(tcb_ctx *, double *muls_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+// hostemu.cpp — TEST INFRASTRUCTURE ONLY.
+// Compiles the __host__ __device__ task code of threshold_crypto_b200/csrc with g++ (scalar
+// Fp2 engine, PTX carry primitives emulated bit-exactly) and exposes the same tcb_* entry
+// points, so the field/curve/pairing/hash LOGIC can be checked against the oracle on a box
+// without a GPU.  It is never loaded by the threshold_crypto_b200 package; the shipped
+// library (libtcb200.so) has no CPU path.
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+#include "../../include/tcb200.h"
+#include "../../threshold_crypto_b200/csrc/scheme.cuh"
+using namespace tcb;
+
+struct tcb_ctx { int dummy; };
+static bool g_ready = false;
+static void ensure() { if (!g_ready) { Consts C; build_consts(C); g_ready = true; } }
+
+extern "C" int tcb_init(tcb_ctx **ctx, const int *, int) { ensure(); *ctx = new tcb_ctx(); return 0; }
+extern "C" void tcb_free(tcb_ctx *ctx) { delete ctx; }
+extern "C" const char *tcb_last_error(const tcb_ctx *) { return ""; }
+extern "C" int tcb_set_engine(tcb_ctx *, int) { return 0; }
+extern "C" uint64_t tcb_launch_count(const tcb_ctx *) { return 0; }
+
+extern "C" int tcb_verify_g2_batch(tcb_ctx *, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
+    for (size_t i = 0; i < n; i++) task_verify_g2<Fp2>(i, a, b, c, d, ok);
+    return 0;
+}
+extern "C" int tcb_hash_g2_batch(tcb_ctx *, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
+    for (size_t i = 0; i < n; i++) task_hash_g2<Fp2>(i, msgs, off, out);
+    return 0;
+}
+extern "C" int tcb_verify_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
+    for (size_t i = 0; i < n; i++) task_verify<Fp2>(i, pk, sig, msgs, off, ok);
+    return 0;
+}
+extern "C" int tcb_sign_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, u8 *out) {
+    for (size_t i = 0; i < n; i++) task_sign<Fp2>(i, sk, msgs, off, nullptr, out);
+    return 0;
+}
+extern "C" int tcb_sign_g2_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *h, u8 *out) {
+    for (size_t i = 0; i < n; i++) task_sign<Fp2>(i, sk, nullptr, nullptr, h, out);
+    return 0;
+}
+extern "C" int tcb_combine_g2_batch(tcb_ctx *, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
+    memset(status, 0, n);
+    if (t == 0) { memcpy(out, shares, n * 192); return 0; }
+    size_t m = t + 1;
+    std::vector<u32> lam(n * m * 8);
+    std::vector<JacStore<Fp2>> terms(n * m);
+    for (size_t i = 0; i < n; i++)
+        for (size_t k = 0; k < m; k++) lagrange_coeff(x + i * m * 32, m, k, &lam[8 * (i * m + k)], status[i]);
+    for (size_t u = 0; u < n * m; u++) task_g2_mul_store<Fp2>(u, lam.data(), shares, terms.data(), status, m);
+    for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, m, terms.data(), out);
+    return 0;
+}
+static int combine_g1(size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status, int mode, const u8 *v, const u64 *voff) {
+    memset(status, 0, n);
+    size_t m = t + 1;
+    std::vector<u32> lam(n * m * 8);
+    std::vector<Jac1Store> terms(n * m);
+    if (t > 0) {
+        for (size_t i = 0; i < n; i++)
+            for (size_t k = 0; k < m; k++) lagrange_coeff(x + i * m * 32, m, k, &lam[8 * (i * m + k)], status[i]);
+        for (size_t u = 0; u < n * m; u++) task_g1_mul_store(u, lam.data(), shares, terms.data(), status, m);
+    }
+    for (size_t i = 0; i < n; i++) {
+        Aff<Fp> g;
+        bool ok = true;
+        if (t > 0) g = g1_sum(i, m, terms.data()); else g = load_g1(shares + 96 * i, ok);
+        if (mode == 0) store_g1(out + 96 * i, g);
+        else xor_with_hash(out + voff[i], g, v + voff[i], (size_t)(voff[i + 1] - voff[i]));
+    }
+    return 0;
+}
+extern "C" int tcb_combine_g1_batch(tcb_ctx *, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
+    return combine_g1(n, t, x, shares, out, status, 0, nullptr, nullptr);
+}
+extern "C" int tcb_decrypt_batch(tcb_ctx *, size_t n, size_t t, const u8 *x, const u8 *shares, const u8 *v, const u64 *voff, u8 *out, u8 *status) {
+    return combine_g1(n, t, x, shares, out, status, 1, v, voff);
+}
+extern "C" int tcb_decrypt_share_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *u, u8 *out) {
+    for (size_t i = 0; i < n; i++) task_g1_mul(i, sk, u, out);
+    return 0;
+}
+extern "C" int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const u8 *sk, u8 *out) {
+    for (size_t i = 0; i < n; i++) task_g1_mul(i, sk, nullptr, out);
+    return 0;
+}
+extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
+    std::vector<Jac1Store> tab(deg + 1);
+    for (size_t c = 0; c <= deg; c++) task_g1_decode(c, coeff, tab.data());
+    for (size_t i = 0; i < n; i++) task_commit_eval(i, deg, tab.data(), x, out);
+    return 0;
+}

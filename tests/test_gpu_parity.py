@@ -1,0 +1,154 @@
+"""GPU (B200): the CUDA kernels through the C ABI (libtcb200.so) against the oracle — bit-exact
+on the same seeded inputs, both engines (lane-pair sliced and one-item-per-thread), the golden
+vectors, the edge cases, and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import cases
+from conftest import fr_bytes, hx, hxs, rand_fr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fp_selftest_on_device(gpu_engine):
+    """PTX carry-chain Montgomery multiply / dot2 / add / sub and the sliced Fp2 ops against the
+    portable CIOS on 2^18 random + edge operands, on the device."""
+    assert gpu_engine.selftest_fp(1 << 18, seed=123) == 0
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_all_entry_points_vs_oracle(gpu_engine, O, engine):
+    gpu_engine.set_engine(engine)
+    cases.check_all(gpu_engine, O, n_sig=37, n_comb=9, t=4, deg=9, n_eval=33, seed=21 + engine)
+    gpu_engine.set_engine(0)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_edges(gpu_engine, O, engine):
+    gpu_engine.set_engine(engine)
+    cases.check_edges(gpu_engine, O)
+    gpu_engine.set_engine(0)
+
+
+def test_golden_vectors(gpu_engine, golden):
+    E = gpu_engine
+    msgs = [bytes.fromhex(m) for m in golden["msgs"]]
+    assert [bytes(p).hex() for p in E.hash_g2_batch(msgs)] == golden["hash_g2"]
+    sk = np.concatenate([hx(s) for s in golden["sk"]])
+    assert [bytes(p).hex() for p in E.g1_mul_gen_batch(sk)] == golden["pk"]
+    nsk = len(golden["sk"])
+    sks = np.concatenate([hx(golden["sk"][i % nsk]) for i in range(len(msgs))])
+    assert [bytes(s).hex() for s in E.sign_batch(sks, msgs)] == golden["sig"]
+    for pi, si, mi, exp in golden["verify_cases"]:
+        assert bool(E.verify_batch(hx(golden["pk"][pi]), hx(golden["sig"][si]), [msgs[mi]])[0]) == exp
+    ts = golden["threshold_sig"]
+    for s in ts["sets"]:
+        out, st = E.combine_g2_batch(1, ts["t"], fr_bytes([i + 1 for i in s["idx"]]), hxs(s["shares"]))
+        assert bytes(out[0]).hex() == s["combined"] and st[0] == 0
+    e = golden["enc"]
+    out, st = E.decrypt_batch(1, 2, fr_bytes([i + 1 for i in e["idx"]]), hxs(e["dshares"]), [bytes.fromhex(e["v"])])
+    assert out[0].hex() == e["plain"]
+    ce = golden["commit_eval"]
+    out = E.commitment_eval_batch(hxs(ce["coeff"]), np.concatenate([hx(x) for x in ce["x"]]))
+    assert [bytes(p).hex() for p in out] == ce["out"]
+    shares = E.commitment_eval_batch(hxs(golden["commitment"]), fr_bytes([i + 1 for i in range(5)]))
+    assert [bytes(p).hex() for p in shares] == golden["pk_shares"]
+
+
+def test_config1_threshold_sig_example(gpu_engine, O):
+    """BASELINE config #1 (examples/threshold_sig.rs path): t=2, n=5, combine the first 3 shares,
+    verify under the master key; a second disjoint-ish subset gives the SAME signature
+    (src/lib.rs:823-873)."""
+    E = gpu_engine
+    rng = np.random.default_rng(99)
+    t, nodes = 2, 5
+    poly = rand_fr(rng, t + 1)
+    msg = b"hey, this is alice"
+    sk_shares = O.poly_eval(poly, fr_bytes([i + 1 for i in range(nodes)]))
+    sig_shares = E.sign_batch(sk_shares, [msg] * nodes)
+    pk_set = E.g1_mul_gen_batch(poly)                     # Poly::commitment
+    pk_shares = E.commitment_eval_batch(pk_set, fr_bytes([i + 1 for i in range(nodes)]))
+    assert E.verify_batch(pk_shares, sig_shares, [msg] * nodes).all()
+    a, _ = E.combine_g2_batch(1, t, fr_bytes([1, 2, 3]), sig_shares[:3])
+    b, _ = E.combine_g2_batch(1, t, fr_bytes([5, 3, 4]), sig_shares[[4, 2, 3]])
+    assert np.array_equal(a, b)
+    assert E.verify_batch(pk_set[0], a[0], [msg])[0] == 1
+    assert E.verify_batch(pk_set[0], a[0], [b"another message"])[0] == 0
+    assert np.array_equal(a, O.combine_g2_batch(1, t, fr_bytes([1, 2, 3]), sig_shares[:3])[0])
+
+
+def test_medium_batch_verify_vs_oracle(gpu_engine, O):
+    """2^10 verifies, every 4th corrupted; oracle runs on all host cores."""
+    import os
+    O.set_threads(os.cpu_count() or 1)
+    n = 1 << 10
+    sk, pk, sig, msgs = cases.make_sig_batch(O, n, 5)
+    exp = O.verify_batch(pk, sig, msgs)
+    got = gpu_engine.verify_batch(pk, sig, msgs)
+    O.set_threads(1)
+    assert np.array_equal(got, exp)
+    assert 0 < exp.sum() < n
+
+
+def test_full_size_properties_config2(gpu_engine, O):
+    """BASELINE config #2 size (2^16 verifies) through size-independent properties: signatures
+    made on the GPU verify on the GPU, corrupted ones do not, and a 2^9 sample is checked
+    bit-exactly against the oracle."""
+    E = gpu_engine
+    n = 1 << 16
+    rng = np.random.default_rng(2)
+    sk = rand_fr(rng, n)
+    msgs = [i.to_bytes(8, "little") * 4 for i in range(n)]
+    pk = E.g1_mul_gen_batch(sk)
+    sig = E.sign_batch(sk, msgs)
+    bad = np.arange(n) % 16 == 5
+    sig_c = sig.copy()
+    sig_c[bad] = np.roll(sig, 1, axis=0)[bad]
+    ok = E.verify_batch(pk, sig_c, msgs)
+    assert np.array_equal(ok.astype(bool), ~bad)
+    sel = rng.choice(n, 512, replace=False)
+    import os
+    O.set_threads(os.cpu_count() or 1)
+    assert np.array_equal(O.sign_batch(sk.reshape(n, 32)[sel].reshape(-1), [msgs[i] for i in sel]), sig[sel])
+    assert np.array_equal(O.verify_batch(pk[sel], sig_c[sel], [msgs[i] for i in sel]), ok[sel])
+    O.set_threads(1)
+
+
+def test_full_size_properties_config3_4_5(gpu_engine, O):
+    """Config #3 (t=10 combine, 2^14 msgs), #4 (t=64 decrypt, 2^12), #5 (deg-1023 evaluate) at a
+    reduced count for the oracle-checked part and the interpolation identity for the rest:
+    combining shares of sk_i * B must give master * B."""
+    E = gpu_engine
+    import os
+    O.set_threads(os.cpu_count() or 1)
+    for (n, t, group) in ((256, 10, 2), (64, 64, 1)):
+        xs, sh, master = cases.make_combine_batch(O, n, t, 40 + t, group=group, extra=21)
+        if group == 2:
+            out, st = E.combine_g2_batch(n, t, xs, sh)
+        else:
+            out, st = E.combine_g1_batch(n, t, xs, sh)
+        assert not st.any() and np.array_equal(out, master)
+    # config #5: degree 1023 at indices 1..64 vs oracle, and f(x)*g1 identity
+    rng = np.random.default_rng(5)
+    coeff = rand_fr(rng, 1024)
+    comm = E.g1_mul_gen_batch(coeff)
+    assert np.array_equal(comm[:8], O.g1_mul_gen_batch(coeff[:8 * 32]))
+    xs = fr_bytes([i + 1 for i in range(64)])
+    out = E.commitment_eval_batch(comm, xs)
+    assert np.array_equal(out, E.g1_mul_gen_batch(O.poly_eval(coeff, xs)))
+    assert np.array_equal(out[:4], O.commitment_eval_batch(comm, xs[:4 * 32]))
+    O.set_threads(1)
+
+
+def test_multi_device_ctx_matches_single(O):
+    """A ctx over all visible devices shards contiguous slices and returns the same bytes."""
+    import torch
+    from threshold_crypto_b200._lib import Engine
+    nd = torch.cuda.device_count()
+    E = Engine(devices=list(range(nd)))
+    sk, pk, sig, msgs = cases.make_sig_batch(O, 23, 77)
+    assert np.array_equal(E.verify_batch(pk, sig, msgs), O.verify_batch(pk, sig, msgs))
+    xs, sh, master = cases.make_combine_batch(O, 7, 3, 78, group=2)
+    out, st = E.combine_g2_batch(7, 3, xs, sh)
+    assert np.array_equal(out, master)
+    E.close()

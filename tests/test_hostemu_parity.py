@@ -1,0 +1,35 @@
+"""CPU: the device task code (threshold_crypto_b200/csrc/*.cuh) compiled for the host
+(tests/hostemu, scalar engine, emulated carry flag) against the oracle and the golden vectors.
+This checks the LOGIC of what the kernels run; the kernels themselves are checked on the GPU
+in test_gpu_parity.py."""
+import numpy as np
+
+import cases
+from conftest import fr_bytes, hx, hxs
+
+
+def test_hostemu_all_entry_points(emu, O):
+    cases.check_all(emu, O, n_sig=5, n_comb=2, t=2, deg=4, n_eval=4, seed=3)
+
+
+def test_hostemu_edges(emu, O):
+    cases.check_edges(emu, O)
+
+
+def test_hostemu_golden(emu, golden):
+    msgs = [bytes.fromhex(m) for m in golden["msgs"]]
+    assert [bytes(p).hex() for p in emu.hash_g2_batch(msgs)] == golden["hash_g2"]
+    sk = np.concatenate([hx(s) for s in golden["sk"]])
+    assert [bytes(p).hex() for p in emu.g1_mul_gen_batch(sk)] == golden["pk"]
+    for pi, si, mi, exp in golden["verify_cases"]:
+        assert bool(emu.verify_batch(hx(golden["pk"][pi]), hx(golden["sig"][si]), [msgs[mi]])[0]) == exp
+    ts = golden["threshold_sig"]
+    for s in ts["sets"]:
+        out, st = emu.combine_g2_batch(1, ts["t"], fr_bytes([i + 1 for i in s["idx"]]), hxs(s["shares"]))
+        assert bytes(out[0]).hex() == s["combined"]
+    e = golden["enc"]
+    out, st = emu.decrypt_batch(1, 2, fr_bytes([i + 1 for i in e["idx"]]), hxs(e["dshares"]), [bytes.fromhex(e["v"])])
+    assert out[0].hex() == e["plain"]
+    ce = golden["commit_eval"]
+    out = emu.commitment_eval_batch(hxs(ce["coeff"]), np.concatenate([hx(x) for x in ce["x"]]))
+    assert [bytes(p).hex() for p in out] == ce["out"]

@@ -1,0 +1,196 @@
+"""ctypes binding of the C ABI declared in include/tcb200.h.
+
+`Engine()` loads the CUDA library `csrc/libtcb200.so` (built by `__graft_entry__.build()` /
+`csrc/build.sh`) and FAILS LOUDLY when it is missing or when no CUDA device is present —
+there is no CPU fallback in this package.  Tests may point `Engine(path)` at the
+host-emulation build under tests/hostemu (test infrastructure, same symbols) to check logic
+on a GPU-less box; that library is never loaded by default.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "csrc", "libtcb200.so")
+
+ENGINE_PAIR = 0
+ENGINE_THREAD = 1
+
+
+class TcbError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def pack_msgs(msgs):
+    """list of bytes -> (concatenated uint8 buffer, uint64 offsets[n+1])"""
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    if len(msgs):
+        off[1:] = np.cumsum([len(m) for m in msgs])
+    buf = np.frombuffer(b"".join(bytes(m) for m in msgs) or b"\0", dtype=np.uint8).copy()
+    return buf, off
+
+
+class Engine:
+    """One tcb_ctx.  Methods mirror include/tcb200.h one to one (numpy uint8 arrays in/out)."""
+
+    def __init__(self, lib_path=None, devices=None):
+        path = lib_path or DEFAULT_LIB
+        if not os.path.exists(path):
+            raise TcbError(
+                f"{path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "threshold_crypto_b200 has no CPU fallback.")
+        self.lib = C.CDLL(path)
+        self.lib.tcb_last_error.restype = C.c_char_p
+        self.lib.tcb_launch_count.restype = C.c_uint64
+        self.ctx = C.c_void_p()
+        if devices is None:
+            rc = self.lib.tcb_init(C.byref(self.ctx), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.tcb_init(C.byref(self.ctx), arr, len(devices))
+        if rc != 0:
+            raise TcbError(f"tcb_init failed (rc={rc}): no usable CUDA device; there is no CPU fallback")
+        self.path = path
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.tcb_free(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TcbError(f"tcb call failed rc={rc}: {self.lib.tcb_last_error(self.ctx).decode()}")
+
+    def set_engine(self, engine):
+        self._ck(self.lib.tcb_set_engine(self.ctx, int(engine)))
+
+    def launch_count(self):
+        return int(self.lib.tcb_launch_count(self.ctx))
+
+    # ---- host-buffer API
+    def verify_g2_batch(self, a_g1, b_g2, c_g1, d_g2):
+        a, b, c, d = _u8(a_g1), _u8(b_g2), _u8(c_g1), _u8(d_g2)
+        n = a.size // 96
+        ok = np.zeros(n, np.uint8)
+        self._ck(self.lib.tcb_verify_g2_batch(self.ctx, C.c_size_t(n), _p(a), _p(b), _p(c), _p(d), _p(ok)))
+        return ok
+
+    def hash_g2_batch(self, msgs):
+        buf, off = pack_msgs(msgs)
+        out = np.zeros((len(msgs), 192), np.uint8)
+        self._ck(self.lib.tcb_hash_g2_batch(self.ctx, C.c_size_t(len(msgs)), _p(buf), _p(off), _p(out)))
+        return out
+
+    def verify_batch(self, pk_g1, sig_g2, msgs):
+        pk, sig = _u8(pk_g1), _u8(sig_g2)
+        buf, off = pack_msgs(msgs)
+        ok = np.zeros(len(msgs), np.uint8)
+        self._ck(self.lib.tcb_verify_batch(self.ctx, C.c_size_t(len(msgs)), _p(pk), _p(sig), _p(buf), _p(off), _p(ok)))
+        return ok
+
+    def sign_batch(self, sk, msgs):
+        sk = _u8(sk)
+        buf, off = pack_msgs(msgs)
+        out = np.zeros((len(msgs), 192), np.uint8)
+        self._ck(self.lib.tcb_sign_batch(self.ctx, C.c_size_t(len(msgs)), _p(sk), _p(buf), _p(off), _p(out)))
+        return out
+
+    def sign_g2_batch(self, sk, h_g2):
+        sk, h = _u8(sk), _u8(h_g2)
+        n = sk.size // 32
+        out = np.zeros((n, 192), np.uint8)
+        self._ck(self.lib.tcb_sign_g2_batch(self.ctx, C.c_size_t(n), _p(sk), _p(h), _p(out)))
+        return out
+
+    def combine_g2_batch(self, n, t, x_fr, shares_g2):
+        x, s = _u8(x_fr), _u8(shares_g2)
+        assert x.size == n * (t + 1) * 32 and s.size == n * (t + 1) * 192
+        out = np.zeros((n, 192), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.tcb_combine_g2_batch(self.ctx, C.c_size_t(n), C.c_size_t(t), _p(x), _p(s), _p(out), _p(st)))
+        return out, st
+
+    def combine_g1_batch(self, n, t, x_fr, shares_g1):
+        x, s = _u8(x_fr), _u8(shares_g1)
+        assert x.size == n * (t + 1) * 32 and s.size == n * (t + 1) * 96
+        out = np.zeros((n, 96), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.tcb_combine_g1_batch(self.ctx, C.c_size_t(n), C.c_size_t(t), _p(x), _p(s), _p(out), _p(st)))
+        return out, st
+
+    def decrypt_share_batch(self, sk, u_g1):
+        sk, u = _u8(sk), _u8(u_g1)
+        n = sk.size // 32
+        out = np.zeros((n, 96), np.uint8)
+        self._ck(self.lib.tcb_decrypt_share_batch(self.ctx, C.c_size_t(n), _p(sk), _p(u), _p(out)))
+        return out
+
+    def decrypt_batch(self, n, t, x_fr, shares_g1, vs):
+        x, s = _u8(x_fr), _u8(shares_g1)
+        buf, off = pack_msgs(vs)
+        out = np.zeros(buf.size, np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.tcb_decrypt_batch(self.ctx, C.c_size_t(n), C.c_size_t(t), _p(x), _p(s), _p(buf), _p(off), _p(out), _p(st)))
+        return [bytes(out[int(off[i]):int(off[i + 1])]) for i in range(n)], st
+
+    def commitment_eval_batch(self, coeff_g1, x_fr):
+        c, x = _u8(coeff_g1), _u8(x_fr)
+        deg = c.size // 96 - 1
+        n = x.size // 32
+        out = np.zeros((n, 96), np.uint8)
+        self._ck(self.lib.tcb_commitment_eval_batch(self.ctx, C.c_size_t(deg), _p(c), C.c_size_t(n), _p(x), _p(out)))
+        return out
+
+    def g1_mul_gen_batch(self, sk):
+        sk = _u8(sk)
+        n = sk.size // 32
+        out = np.zeros((n, 96), np.uint8)
+        self._ck(self.lib.tcb_g1_mul_gen_batch(self.ctx, C.c_size_t(n), _p(sk), _p(out)))
+        return out
+
+    # ---- self-test / probes (CUDA library only)
+    def selftest_fp(self, n=1 << 16, seed=1):
+        rc = self.lib.tcb_selftest_fp(self.ctx, C.c_size_t(n), C.c_uint64(seed))
+        if rc < 0:
+            self._ck(rc)
+        return rc
+
+    def probe_imad(self):
+        v = C.c_double()
+        self._ck(self.lib.tcb_probe_imad(self.ctx, C.byref(v)))
+        return v.value
+
+    def probe_fpmul(self):
+        v = C.c_double()
+        self._ck(self.lib.tcb_probe_fpmul(self.ctx, C.byref(v)))
+        return v.value
+
+    # ---- device-pointer API (ints are raw device addresses, stream is a cudaStream_t as int)
+    def dev_call(self, name, stream, *args):
+        fn = getattr(self.lib, name)
+        cargs = [self.ctx, C.c_void_p(stream)]
+        for a in args:
+            if isinstance(a, tuple):      # ("size", value)
+                cargs.append(C.c_size_t(a[1]) if a[0] == "size" else C.c_uint64(a[1]))
+            elif a is None:
+                cargs.append(None)
+            else:
+                cargs.append(C.c_void_p(int(a)))
+        self._ck(fn(*cargs))

@@ -1,0 +1,456 @@
+// scheme.cuh — per-item "tasks" of the threshold_crypto hot path,
+// written once as __host__ __device__ templates over the Fp2 engine.  kernels.cu launches
+// them one item per thread (Fp2) or one item per lane pair (Fp2S); tests/hostemu runs the
+// scalar instantiation on the CPU for logic checks only.
+//
+// Byte formats are the C-ABI's (include/tcb200.h): EXTERNAL pairing's uncompressed affine
+// big-endian encodings and canonical little-endian Fr (src/serde_impl.rs:109,296).
+#pragma once
+#include "tower.cuh"
+
+namespace tcb {
+
+template <class F2> TCB_HD bool is_writer() {
+#if defined(__CUDA_ARCH__)
+    return !F2::SLICED || (threadIdx.x & 1u) == 0;
+#else
+    return true;
+#endif
+}
+template <class F2> TCB_HD u32 my_role() {
+#if defined(__CUDA_ARCH__)
+    return F2::SLICED ? (threadIdx.x & 1u) : 0u;
+#else
+    return 0u;
+#endif
+}
+
+// ----------------------------------------------------------------------------- codecs
+// 48-byte big-endian canonical -> Montgomery.  ok=false if the integer is >= p.
+TCB_HD Fp load_fp_be(const u8 *b, bool &ok) {
+    Fp t;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const u8 *q = b + (11 - i) * 4;
+        t.l[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+    }
+    ok = ok && limbs_lt_mod<FpParams>(t.l);
+    return fp_to_mont(t);
+}
+TCB_HD void store_fp_be(u8 *b, const Fp &a) {
+    Fp t = fp_from_mont(a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        u8 *q = b + (11 - i) * 4;
+        q[0] = (u8)(t.l[i] >> 24); q[1] = (u8)(t.l[i] >> 16); q[2] = (u8)(t.l[i] >> 8); q[3] = (u8)t.l[i];
+    }
+}
+// G1 uncompressed 96 B: x || y, byte0 bit 0x40 = infinity
+TCB_HD Aff<Fp> load_g1(const u8 *b, bool &ok) {
+    Aff<Fp> a;
+    if (b[0] & 0x40) { a.inf = true; a.x = Fp::zero(); a.y = Fp::zero(); return a; }
+    a.inf = false;
+    a.x = load_fp_be(b, ok);
+    a.y = load_fp_be(b + 48, ok);
+    return a;
+}
+TCB_HD void store_g1(u8 *b, const Aff<Fp> &a) {
+    if (a.inf) { for (int i = 0; i < 96; i++) b[i] = 0; b[0] = 0x40; return; }
+    store_fp_be(b, a.x);
+    store_fp_be(b + 48, a.y);
+}
+// Fp2 as c1 || c0 (96 B); a sliced engine only touches its own half
+template <class F2>
+TCB_HD F2 load_f2_be(const u8 *b, bool &ok) {
+    if (F2::SLICED) {
+        Fp h = load_fp_be(b + (my_role<F2>() ? 0 : 48), ok);
+        return F2::from_halves(h, h);
+    }
+    Fp c1 = load_fp_be(b, ok), c0 = load_fp_be(b + 48, ok);
+    return F2::from_halves(c0, c1);
+}
+template <class F2>
+TCB_HD void store_f2_be(u8 *b, const F2 &a) {
+    if (F2::SLICED) {
+        // each lane writes its own half
+        Fp2c t; a.store(t);
+        if (my_role<F2>()) store_fp_be(b, t.c1); else store_fp_be(b + 48, t.c0);
+        return;
+    }
+    Fp2c t; a.store(t);
+    store_fp_be(b, t.c1);
+    store_fp_be(b + 48, t.c0);
+}
+// G2 uncompressed 192 B: x.c1 || x.c0 || y.c1 || y.c0
+template <class F2>
+TCB_HD Aff<F2> load_g2(const u8 *b, bool &ok) {
+    Aff<F2> a;
+    if (b[0] & 0x40) { a.inf = true; a.x = F2::zero(); a.y = F2::zero(); return a; }
+    a.inf = false;
+    a.x = load_f2_be<F2>(b, ok);
+    a.y = load_f2_be<F2>(b + 96, ok);
+    return a;
+}
+template <class F2>
+TCB_HD void store_g2(u8 *b, const Aff<F2> &a) {
+    if (a.inf) {
+        if (is_writer<F2>()) { for (int i = 0; i < 192; i++) b[i] = 0; b[0] = 0x40; }
+        return;
+    }
+    store_f2_be<F2>(b, a.x);
+    store_f2_be<F2>(b + 96, a.y);
+}
+// canonical LE 32-byte scalar -> 8 u32 limbs (no reduction; caller guarantees < r or accepts k mod group order)
+TCB_HD void load_scalar_le(u32 *k, const u8 *b) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) k[i] = (u32)b[4 * i] | ((u32)b[4 * i + 1] << 8) | ((u32)b[4 * i + 2] << 16) | ((u32)b[4 * i + 3] << 24);
+}
+// G1 compressed 48 B: flags 0x80 compressed, 0x40 infinity, 0x20 y > -y
+TCB_HD void g1_compress(u8 *out, const Aff<Fp> &a) {
+    if (a.inf) { for (int i = 0; i < 48; i++) out[i] = 0; out[0] = 0xc0; return; }
+    store_fp_be(out, a.x);
+    out[0] |= 0x80;
+    if (fp_cmp(a.y, -a.y) > 0) out[0] |= 0x20;
+}
+
+// ----------------------------------------------------------------------------- SHA3-256 (FIPS 202) and ChaCha20 word stream
+TCB_HD u64 rotl64(u64 v, int n) { return n ? ((v << n) | (v >> (64 - n))) : v; }
+TCB_HDN void keccak_f(u64 *s) {
+    const u64 RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+        0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+        0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    for (int rnd = 0; rnd < 24; rnd++) {
+        u64 c[5], b[25];
+        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+        for (int x = 0; x < 5; x++) {
+            u64 d = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+            for (int y = 0; y < 25; y += 5) s[y + x] ^= d;
+        }
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(s[x + 5 * y], ROT[x + 5 * y]);
+        for (int y = 0; y < 25; y += 5)
+            for (int x = 0; x < 5; x++) s[y + x] = b[y + x] ^ (~b[y + (x + 1) % 5] & b[y + (x + 2) % 5]);
+        s[0] ^= RC[rnd];
+    }
+}
+// SHA3-256 of the concatenation m1 || m2 (either may be empty); src/util.rs:3-9
+TCB_HDN void sha3_256(const u8 *m1, size_t l1, const u8 *m2, size_t l2, u8 *out) {
+    u64 s[25];
+    for (int i = 0; i < 25; i++) s[i] = 0;
+    size_t pos = 0;   // byte position inside the 136-byte rate block
+    for (size_t i = 0; i < l1 + l2; i++) {
+        u8 v = i < l1 ? m1[i] : m2[i - l1];
+        s[pos >> 3] ^= (u64)v << (8 * (pos & 7));
+        if (++pos == 136) { keccak_f(s); pos = 0; }
+    }
+    s[pos >> 3] ^= (u64)0x06 << (8 * (pos & 7));
+    s[16] ^= 0x8000000000000000ULL;
+    keccak_f(s);
+    for (int i = 0; i < 32; i++) out[i] = (u8)(s[i >> 3] >> (8 * (i & 7)));
+}
+// rand_chacha 0.2 ChaChaRng::from_seed + BlockRng word stream
+struct ChaChaRng {
+    u32 key[8];
+    u32 buf[16];
+    u64 ctr;
+    int idx;
+};
+TCB_HD u32 rotl32(u32 v, int n) { return (v << n) | (v >> (32 - n)); }
+#define TCB_QR(a, b, c, d) a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); a += b; d ^= a; d = rotl32(d, 8); c += d; b ^= c; b = rotl32(b, 7);
+TCB_HDN void chacha_refill(ChaChaRng &g) {
+    u32 s[16], w[16];
+    s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
+    for (int i = 0; i < 8; i++) s[4 + i] = g.key[i];
+    s[12] = (u32)g.ctr; s[13] = (u32)(g.ctr >> 32); s[14] = 0; s[15] = 0;
+    for (int i = 0; i < 16; i++) w[i] = s[i];
+    for (int i = 0; i < 10; i++) {
+        TCB_QR(w[0], w[4], w[8], w[12]) TCB_QR(w[1], w[5], w[9], w[13]) TCB_QR(w[2], w[6], w[10], w[14]) TCB_QR(w[3], w[7], w[11], w[15])
+        TCB_QR(w[0], w[5], w[10], w[15]) TCB_QR(w[1], w[6], w[11], w[12]) TCB_QR(w[2], w[7], w[8], w[13]) TCB_QR(w[3], w[4], w[9], w[14])
+    }
+    for (int i = 0; i < 16; i++) g.buf[i] = w[i] + s[i];
+    g.ctr++;
+    g.idx = 0;
+}
+TCB_HD void rng_seed(ChaChaRng &g, const u8 *seed) {
+    for (int i = 0; i < 8; i++) g.key[i] = (u32)seed[4 * i] | ((u32)seed[4 * i + 1] << 8) | ((u32)seed[4 * i + 2] << 16) | ((u32)seed[4 * i + 3] << 24);
+    g.ctr = 0;
+    g.idx = 16;
+}
+TCB_HD u32 rng_u32(ChaChaRng &g) {
+    if (g.idx >= 16) chacha_refill(g);
+    return g.buf[g.idx++];
+}
+// ff_derive 0.6 Field::random for Fq (A1): 6 next_u64 = 12 consecutive words, top limb >> 3,
+// reject >= p; the raw limbs ARE the Montgomery representation.
+TCB_HD Fp fp_random(ChaChaRng &g) {
+    Fp r;
+    for (;;) {
+        for (int i = 0; i < 12; i++) r.l[i] = rng_u32(g);
+        r.l[11] &= 0x1fffffffu;
+        if (limbs_lt_mod<FpParams>(r.l)) return r;
+    }
+}
+// EXTERNAL pairing 0.16 G2::random (A2, A3) followed by the exact-cofactor multiplication.
+template <class F2>
+TCB_HDN Jac<F2> g2_random(ChaChaRng &g) {
+    const Consts &C = CONSTS();
+    F2 b2 = F2::from_halves(C.b1, C.b1);   // 4 (1 + u)
+    for (;;) {
+        Fp c0 = fp_random(g);
+        Fp c1 = fp_random(g);
+        bool greatest = (rng_u32(g) & 1u) != 0;
+        F2 x = F2::from_halves(c0, c1);
+        F2 y;
+        if (!fp2_sqrt(y, sqr(x) * x + b2)) continue;
+        F2 ny = -y;
+        bool pick_y = (fp2_cmp(y, ny) < 0) != greatest;
+        Aff<F2> a;
+        a.x = x; a.y = select(pick_y, y, ny); a.inf = false;
+        Jac<F2> p = jac_mul_const<F2, ExpH2>(a);
+        if (!jac_is_inf(p)) return p;
+    }
+}
+template <class F2>
+TCB_HD Jac<F2> hash_g2(const u8 *m1, size_t l1, const u8 *m2, size_t l2) {   // src/lib.rs:691-694
+    u8 digest[32];
+    sha3_256(m1, l1, m2, l2, digest);
+    ChaChaRng g;
+    rng_seed(g, digest);
+    return g2_random<F2>(g);
+}
+template <class F2>
+TCB_HD Jac<F2> hash_g1_g2(const Aff<Fp> &g1, const u8 *msg, size_t len) {   // src/lib.rs:697-707
+    u8 comp[48], d[32];
+    g1_compress(comp, g1);
+    if (len > 64) {
+        sha3_256(msg, len, msg, 0, d);
+        return hash_g2<F2>(d, 32, comp, 48);
+    }
+    return hash_g2<F2>(msg, len, comp, 48);
+}
+// src/lib.rs:710-715: one keystream u32 per output byte (`next_u32() as u8`, A5)
+TCB_HD void xor_with_hash(u8 *out, const Aff<Fp> &g1, const u8 *in, size_t len) {
+    u8 comp[48], d[32];
+    g1_compress(comp, g1);
+    sha3_256(comp, 48, comp, 0, d);
+    ChaChaRng g;
+    rng_seed(g, d);
+    for (size_t i = 0; i < len; i++) out[i] = (u8)rng_u32(g) ^ in[i];
+}
+
+// ----------------------------------------------------------------------------- Fr helpers
+TCB_HD Fr fr_one() { return CONSTS().fr_r1; }
+TCB_HD Fr fr_load_le(const u8 *b, bool &ok) {
+    Fr t;
+    load_scalar_le(t.l, b);
+    ok = ok && limbs_lt_mod<FrParams>(t.l);
+    return t * CONSTS().fr_r2;
+}
+TCB_HD Fr fr_inv(const Fr &a) {
+    Fr acc = fr_one();
+    for (int i = 255; i >= 0; i--) {
+        acc = acc * acc;
+        if ((ExpRm2::get(i >> 5) >> (i & 31)) & 1) acc = acc * a;
+    }
+    return acc;
+}
+// lambda_i(0) for sample i of item `xs` (m = t+1 canonical LE scalars), exactly the value
+// src/lib.rs:739-765 produces: numerator = prod_{j != i} x_j (by position), denominator =
+// prod_{x_j != x_i} (x_j - x_i) (by value — duplicates are skipped, never a zero divisor).
+// Output: canonical little-endian limbs.  status 3 if an x is not a canonical Fr.
+TCB_HDN void lagrange_coeff(const u8 *xs, size_t m, size_t i, u32 *out, u8 &status) {
+    bool ok = true;
+    Fr xi = fr_load_le(xs + 32 * i, ok);
+    Fr num = fr_one(), den = fr_one();
+    for (size_t j = 0; j < m; j++) {
+        Fr xj = fr_load_le(xs + 32 * j, ok);
+        if (j != i) num = num * xj;
+        if (xj != xi) den = den * (xj - xi);
+    }
+    Fr l = from_mont<FrParams>(num * fr_inv(den));
+    for (int k = 0; k < 8; k++) out[k] = l.l[k];
+    if (!ok) status = 3;
+}
+
+// ----------------------------------------------------------------------------- per-item tasks
+// a1: e(a,b) == e(c,d); c == nullptr means the G1 generator (src/lib.rs:108-110,182-186,508-512)
+template <class F2>
+TCB_HD void task_verify_g2(size_t i, const u8 *a_g1, const u8 *b_g2, const u8 *c_g1, const u8 *d_g2, u8 *ok_out) {
+    bool ok = true;
+    Aff<Fp> a = load_g1(a_g1 + 96 * i, ok);
+    Aff<F2> b = load_g2<F2>(b_g2 + 192 * i, ok);
+    Aff<Fp> c;
+    if (c_g1) c = load_g1(c_g1 + 96 * i, ok);
+    else { c.x = CONSTS().g1x; c.y = CONSTS().g1y; c.inf = false; }
+    Aff<F2> d = load_g2<F2>(d_g2 + 192 * i, ok);
+    bool res = pairing_eq<F2>(a, b, c, d);
+    if (is_writer<F2>()) ok_out[i] = (res && ok) ? 1 : 0;
+}
+// a2: hash_g2 -> uncompressed affine G2
+template <class F2>
+TCB_HD void task_hash_g2(size_t i, const u8 *msgs, const u64 *off, u8 *out_g2) {
+    Jac<F2> h = hash_g2<F2>(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0);
+    store_g2<F2>(out_g2 + 192 * i, jac_to_aff(h));
+}
+// a3: PublicKey::verify = hash_g2 then a1 (src/lib.rs:115-117)
+template <class F2>
+TCB_HD void task_verify(size_t i, const u8 *pk_g1, const u8 *sig_g2, const u8 *msgs, const u64 *off, u8 *ok_out) {
+    bool ok = true;
+    Aff<Fp> pk = load_g1(pk_g1 + 96 * i, ok);
+    Aff<F2> sig = load_g2<F2>(sig_g2 + 192 * i, ok);
+    Aff<F2> h = jac_to_aff(hash_g2<F2>(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0));
+    Aff<Fp> g;
+    g.x = CONSTS().g1x; g.y = CONSTS().g1y; g.inf = false;
+    bool res = pairing_eq<F2>(pk, h, g, sig);
+    if (is_writer<F2>()) ok_out[i] = (res && ok) ? 1 : 0;
+}
+// a4: sign = sk * hash_g2(msg) (src/lib.rs:372-381); h_g2 != nullptr selects sign_g2
+template <class F2>
+TCB_HD void task_sign(size_t i, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h_g2, u8 *out_g2) {
+    u32 k[8];
+    load_scalar_le(k, sk + 32 * i);
+    bool ok = true;
+    Aff<F2> h = h_g2 ? load_g2<F2>(h_g2 + 192 * i, ok)
+                     : jac_to_aff(hash_g2<F2>(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0));
+    store_g2<F2>(out_g2 + 192 * i, jac_to_aff(jac_mul_aff<F2, 8>(h, k)));
+}
+// generic k * P over G2 with the result kept Jacobian in a Montgomery scratch array
+// (used for the per-share terms of interpolate, src/lib.rs:753-765)
+template <class F2> struct JacStore { Fp2c x, y, z; };
+template <class F2>
+TCB_HD void task_g2_mul_store(size_t i, const u32 *k_limbs, const u8 *pts_g2, JacStore<F2> *out, u8 *status, size_t per_item) {
+    bool ok = true;
+    Aff<F2> p = load_g2<F2>(pts_g2 + 192 * i, ok);
+    Jac<F2> r = jac_mul_aff<F2, 8>(p, k_limbs + 8 * i);
+    r.x.store(out[i].x); r.y.store(out[i].y); r.z.store(out[i].z);
+    if (!ok && is_writer<F2>()) status[i / per_item] = 3;
+}
+template <class F2>
+TCB_HD void task_g2_sum(size_t i, size_t m, const JacStore<F2> *terms, u8 *out_g2) {
+    Jac<F2> acc = jac_inf<F2>();
+    for (size_t k = 0; k < m; k++) {
+        const JacStore<F2> &t = terms[i * m + k];
+        Jac<F2> p;
+        p.x = F2::load(t.x); p.y = F2::load(t.y); p.z = F2::load(t.z);
+        acc = jac_add(acc, p);
+    }
+    store_g2<F2>(out_g2 + 192 * i, jac_to_aff(acc));
+}
+// t == 0 shortcut of interpolate (src/lib.rs:735-737): the first sample is returned unchanged
+template <class F2>
+TCB_HD void task_g2_copy(size_t i, const u8 *in, u8 *out) {
+    if (is_writer<F2>()) for (int k = 0; k < 192; k++) out[192 * i + k] = in[192 * i + k];
+}
+
+// ---- G1 tasks (always one item per thread)
+struct Jac1Store { Fp x, y, z; };
+TCB_HD void task_g1_mul(size_t i, const u8 *sk, const u8 *pts_g1, u8 *out_g1) {   // a7 share / a9
+    u32 k[8];
+    load_scalar_le(k, sk + 32 * i);
+    bool ok = true;
+    Aff<Fp> p;
+    if (pts_g1) p = load_g1(pts_g1 + 96 * i, ok);
+    else { p.x = CONSTS().g1x; p.y = CONSTS().g1y; p.inf = false; }
+    store_g1(out_g1 + 96 * i, jac_to_aff(jac_mul_aff<Fp, 8>(p, k)));
+}
+TCB_HD void task_g1_mul_store(size_t i, const u32 *k_limbs, const u8 *pts_g1, Jac1Store *out, u8 *status, size_t per_item) {
+    bool ok = true;
+    Aff<Fp> p = load_g1(pts_g1 + 96 * i, ok);
+    Jac<Fp> r = jac_mul_aff<Fp, 8>(p, k_limbs + 8 * i);
+    out[i].x = r.x; out[i].y = r.y; out[i].z = r.z;
+    if (!ok) status[i / per_item] = 3;
+}
+TCB_HD Aff<Fp> g1_sum(size_t i, size_t m, const Jac1Store *terms) {
+    Jac<Fp> acc = jac_inf<Fp>();
+    for (size_t k = 0; k < m; k++) {
+        Jac<Fp> p;
+        p.x = terms[i * m + k].x; p.y = terms[i * m + k].y; p.z = terms[i * m + k].z;
+        acc = jac_add(acc, p);
+    }
+    return jac_to_aff(acc);
+}
+// a8: Commitment::evaluate (src/poly.rs:497-508): Horner, acc = acc * x + C_k
+TCB_HD void task_commit_eval(size_t i, size_t deg, const Jac1Store *coeff, const u8 *x_fr, u8 *out_g1) {
+    u32 k[8];
+    load_scalar_le(k, x_fr + 32 * i);
+    Jac<Fp> acc;
+    acc.x = coeff[deg].x; acc.y = coeff[deg].y; acc.z = coeff[deg].z;
+    for (size_t c = deg; c-- > 0;) {
+        acc = jac_mul_jac<Fp, 8>(acc, k);
+        Jac<Fp> ck;
+        ck.x = coeff[c].x; ck.y = coeff[c].y; ck.z = coeff[c].z;
+        acc = jac_add(acc, ck);
+    }
+    store_g1(out_g1 + 96 * i, jac_to_aff(acc));
+}
+TCB_HD void task_g1_decode(size_t i, const u8 *pts_g1, Jac1Store *out) {
+    bool ok = true;
+    Jac<Fp> p = jac_from_aff(load_g1(pts_g1 + 96 * i, ok));
+    out[i].x = p.x; out[i].y = p.y; out[i].z = p.z;
+}
+
+// ----------------------------------------------------------------------------- constants builder (host side; runs at tcb_init)
+// Computes every derived constant from p, r and the generator coordinates using the same
+// field code, so nothing but the curve definition is hard-coded.
+inline void limbs_from_hex(u32 *l, int n, const char *hex) {
+    for (int i = 0; i < n; i++) l[i] = 0;
+    int len = 0;
+    while (hex[len]) len++;
+    for (int i = 0; i < len; i++) {
+        char c = hex[len - 1 - i];
+        u32 v = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+        l[i / 8] |= v << (4 * (i % 8));
+    }
+}
+template <class P>
+inline Mont<P> pow2_mod(int bits) {
+    Mont<P> r = Mont<P>::zero();
+    r.l[0] = 1;
+    for (int i = 0; i < bits; i++) r = madd<P>(r, r);
+    return r;
+}
+inline void build_consts(Consts &C) {
+    C.r1 = pow2_mod<FpParams>(384);
+    C.r2 = pow2_mod<FpParams>(768);
+    C.fr_r1 = pow2_mod<FrParams>(256);
+    C.fr_r2 = pow2_mod<FrParams>(512);
+    h_consts.r1 = C.r1; h_consts.r2 = C.r2; h_consts.fr_r1 = C.fr_r1; h_consts.fr_r2 = C.fr_r2;
+    Fp four = Fp::zero();
+    four.l[0] = 4;
+    C.b1 = fp_to_mont(four);
+    Fp t;
+    limbs_from_hex(t.l, 12, "17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"); C.g1x = fp_to_mont(t);
+    limbs_from_hex(t.l, 12, "08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1"); C.g1y = fp_to_mont(t);
+    limbs_from_hex(t.l, 12, "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8"); C.g2x.c0 = fp_to_mont(t);
+    limbs_from_hex(t.l, 12, "13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"); C.g2x.c1 = fp_to_mont(t);
+    limbs_from_hex(t.l, 12, "0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801"); C.g2y.c0 = fp_to_mont(t);
+    limbs_from_hex(t.l, 12, "0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be"); C.g2y.c1 = fp_to_mont(t);
+    // Frobenius: g1 = xi^((p-1)/6) (computed by repeated squaring over the exponent bits),
+    // g2 = g1 * conj(g1), g3 = g2 * g1; frob[k][m] = gk^m
+    u32 e[12];
+    limbs_from_hex(e, 12, "1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaaa");
+    {   // e = (p - 1) / 6
+        u64 rem = 0;
+        for (int i = 11; i >= 0; i--) { u64 cur = (rem << 32) | e[i]; e[i] = (u32)(cur / 6); rem = cur % 6; }
+    }
+    Fp2 xi = Fp2::from_halves(C.r1, C.r1), g[4];
+    g[1] = Fp2::one();
+    bool started = false;
+    for (int i = 383; i >= 0; i--) {
+        if (started) g[1] = sqr(g[1]);
+        if ((e[i >> 5] >> (i & 31)) & 1) { g[1] = started ? g[1] * xi : xi; started = true; }
+    }
+    g[2] = g[1] * conj(g[1]);
+    g[3] = g[2] * g[1];
+    for (int k = 1; k <= 3; k++) {
+        Fp2 acc = Fp2::one();
+        for (int m = 0; m < 6; m++) { acc.store(C.frob[k][m]); acc = acc * g[k]; }
+    }
+    for (int m = 0; m < 6; m++) Fp2::one().store(C.frob[0][m]);
+    h_consts = C;
+}
+
+}  // namespace tcb

@@ -1,0 +1,643 @@
+// tower.cuh — Fp2 / Fp6 / Fp12 tower, Jacobian curve arithmetic and the optimal-ate pairing
+// check, templated over the Fp2 implementation:
+//   * Fp2   — one element per thread (c0, c1 both in the thread's registers);
+//   * Fp2S  — "lane-pair sliced": lane 2k holds c0, lane 2k+1 holds c1 of the SAME element,
+//             products are one lazy-reduced dot product per lane (a0*b0 + a1*(-b1) |
+//             a0*b1 + a1*b0) with the partner half fetched by warp shuffles.  Halves the
+//             per-thread state of every G2 / Fp12 value and doubles the threads per item.
+// All tower code above Fp2 is written once against that interface.
+//
+// What the reference computes with these (EXTERNAL pairing 0.16, call sites in
+// /root/reference/src/lib.rs:108-110,185,511): e(A,B) == e(C,D).  Here that is evaluated as
+// FE( ML(A,B) * ML(-C,D) ) == 1 with one shared Miller-loop accumulator and one final
+// exponentiation (cyclotomic squarings in the hard part) — same boolean, ~half the work.
+#pragma once
+#include "fp.cuh"
+
+namespace tcb {
+
+// ----------------------------------------------------------------------------- constants (host-built, device __constant__)
+struct Fp2c { Fp c0, c1; };   // plain storage form of an Fp2 element
+struct Consts {
+    Fp r1;            // R mod p  (Montgomery one)
+    Fp r2;            // R^2 mod p
+    Fp b1;            // 4 (G1 curve b), Montgomery
+    Fp2c frob[4][6];  // frob[k][m] = xi^(m (p^k - 1)/6)
+    Fp g1x, g1y;      // G1 generator
+    Fp2c g2x, g2y;    // G2 generator
+    Fr fr_r1, fr_r2;  // Fr Montgomery constants
+    // GLV / misc constants can be appended here
+};
+#if defined(__CUDACC__)
+__device__ __constant__ Consts d_consts;
+#endif
+static Consts h_consts;
+TCB_HD const Consts &CONSTS() {
+#if defined(__CUDA_ARCH__)
+    return d_consts;
+#else
+    return h_consts;
+#endif
+}
+
+// big-exponent tables (little-endian u32 limbs), same on host and device
+#define TCB_EXP_TABLE(NAME, NLIMBS, ...)                              \
+    struct NAME { static constexpr int N = NLIMBS;                    \
+                  TCB_HD static u32 get(int i) { const u32 t[NLIMBS] = {__VA_ARGS__}; return t[i]; } };
+// p - 2
+TCB_EXP_TABLE(ExpPm2, 12, 0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau)
+// (p - 3) / 4
+TCB_EXP_TABLE(ExpPm3d4, 12, 0xffffeaaau, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u, 0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au)
+// (p - 1) / 2
+TCB_EXP_TABLE(ExpPm1d2, 12, 0xffffd555u, 0xdcff7fffu, 0x58a9ffffu, 0x0f55ffffu, 0x7b587b12u, 0xb3986950u, 0x79c2895fu, 0xb23ba5c2u, 0x21a5d66bu, 0x258dd3dbu, 0x1cbff34du, 0x0d0088f5u)
+// (p + 1) / 4
+TCB_EXP_TABLE(ExpPp1d4, 12, 0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u, 0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au)
+// G2 cofactor h2 (EXTERNAL pairing scale_by_cofactor), 507 bits
+TCB_EXP_TABLE(ExpH2, 16, 0x1c7238e5u, 0xcf1c38e3u, 0x786f0c70u, 0x1616ec6eu, 0x3a6691aeu, 0x21537e29u, 0x4d9e82efu, 0xa628f1cbu, 0x2e5a7ddfu, 0xa68a205bu, 0x47085abau, 0xcd91de45u, 0x2876a202u, 0x091d5079u, 0x5414e7f1u, 0x05d543a9u)
+// r (group order) for subgroup checks
+TCB_EXP_TABLE(ExpR, 8, 0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u)
+// r - 2
+TCB_EXP_TABLE(ExpRm2, 8, 0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u)
+
+#define TCB_BLS_X 0xd201000000010000ULL
+
+TCB_HD Fp fp_one() { return CONSTS().r1; }
+
+template <class E>
+TCB_HDN Fp fp_pow(const Fp &a) {
+    Fp acc = fp_one();
+    bool started = false;
+    for (int i = E::N * 32 - 1; i >= 0; i--) {
+        if (started) acc = sqr(acc);
+        if ((E::get(i >> 5) >> (i & 31)) & 1) {
+            if (started) acc = acc * a; else { acc = a; started = true; }
+        }
+    }
+    return acc;
+}
+TCB_HD Fp fp_inv(const Fp &a) { return fp_pow<ExpPm2>(a); }
+TCB_HD Fp fp_to_mont(const Fp &a) { return a * CONSTS().r2; }
+TCB_HD Fp fp_from_mont(const Fp &a) { return from_mont<FpParams>(a); }
+// canonical compare of two Montgomery-form elements
+TCB_HD int fp_cmp(const Fp &a, const Fp &b) {
+    Fp ca = fp_from_mont(a), cb = fp_from_mont(b);
+    return limbs_cmp<12>(ca.l, cb.l);
+}
+
+// ----------------------------------------------------------------------------- lane helpers
+#if defined(__CUDACC__)
+TCB_D u32 lane_role() { return threadIdx.x & 1u; }
+TCB_D u32 pair_mask() { return 3u << (threadIdx.x & 30u); }
+TCB_D Fp partner(const Fp &a) {
+    Fp r;
+    u32 m = pair_mask();
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = __shfl_xor_sync(m, a.l[i], 1);
+    return r;
+}
+TCB_D bool pair_and(bool v) { u32 m = pair_mask(); return v && __shfl_xor_sync(m, (int)v, 1); }
+#endif
+
+// ----------------------------------------------------------------------------- Fp2, one element per thread
+struct Fp2 {
+    Fp c0, c1;
+    static constexpr bool SLICED = false;
+    TCB_HD static Fp2 zero() { Fp2 r; r.c0 = Fp::zero(); r.c1 = Fp::zero(); return r; }
+    TCB_HD static Fp2 one() { Fp2 r; r.c0 = fp_one(); r.c1 = Fp::zero(); return r; }
+    TCB_HD static Fp2 load(const Fp2c &c) { Fp2 r; r.c0 = c.c0; r.c1 = c.c1; return r; }
+    TCB_HD static Fp2 from_halves(const Fp &c0, const Fp &c1) { Fp2 r; r.c0 = c0; r.c1 = c1; return r; }
+    TCB_HD void store(Fp2c &c) const { c.c0 = c0; c.c1 = c1; }
+    TCB_HD void gather(Fp &o0, Fp &o1) const { o0 = c0; o1 = c1; }
+};
+TCB_HD Fp2 operator+(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+TCB_HD Fp2 operator-(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+TCB_HD Fp2 operator-(const Fp2 &a) { Fp2 r; r.c0 = -a.c0; r.c1 = -a.c1; return r; }
+TCB_HD Fp2 dbl(const Fp2 &a) { return a + a; }
+TCB_HD Fp2 conj(const Fp2 &a) { Fp2 r; r.c0 = a.c0; r.c1 = -a.c1; return r; }
+TCB_HD Fp2 operator*(const Fp2 &a, const Fp2 &b) {
+    Fp2 r;
+    r.c0 = dot2(a.c0, b.c0, a.c1, -b.c1);
+    r.c1 = dot2(a.c0, b.c1, a.c1, b.c0);
+    return r;
+}
+TCB_HD Fp2 sqr(const Fp2 &a) {
+    Fp2 r;
+    Fp m = a.c0 * a.c1;
+    r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
+    r.c1 = dbl(m);
+    return r;
+}
+TCB_HD Fp2 mul_fp(const Fp2 &a, const Fp &k) { Fp2 r; r.c0 = a.c0 * k; r.c1 = a.c1 * k; return r; }
+TCB_HD Fp2 mul_xi(const Fp2 &a) { Fp2 r; r.c0 = a.c0 - a.c1; r.c1 = a.c0 + a.c1; return r; }
+TCB_HD bool is_zero(const Fp2 &a) { return a.c0.is_zero() && a.c1.is_zero(); }
+TCB_HD bool eq(const Fp2 &a, const Fp2 &b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+TCB_HD Fp2 select(bool c, const Fp2 &a, const Fp2 &b) { return c ? a : b; }
+TCB_HD Fp norm(const Fp2 &a) { return dot2(a.c0, a.c0, a.c1, a.c1); }
+TCB_HD Fp2 inv(const Fp2 &a) {
+    Fp n = fp_inv(norm(a));
+    Fp2 r; r.c0 = a.c0 * n; r.c1 = -(a.c1 * n); return r;
+}
+
+#if defined(__CUDACC__)
+// ----------------------------------------------------------------------------- Fp2S, sliced over a lane pair (device only)
+struct Fp2S {
+    Fp h;   // lane role 0: c0, role 1: c1
+    static constexpr bool SLICED = true;
+    TCB_D static Fp2S zero() { Fp2S r; r.h = Fp::zero(); return r; }
+    TCB_D static Fp2S one() { Fp2S r; r.h = lane_role() ? Fp::zero() : fp_one(); return r; }
+    TCB_D static Fp2S load(const Fp2c &c) { Fp2S r; r.h = lane_role() ? c.c1 : c.c0; return r; }
+    TCB_D static Fp2S from_halves(const Fp &c0, const Fp &c1) { Fp2S r; r.h = lane_role() ? c1 : c0; return r; }
+    TCB_D void store(Fp2c &c) const { if (lane_role()) c.c1 = h; else c.c0 = h; }
+    TCB_D void gather(Fp &o0, Fp &o1) const { Fp o = partner(h); bool r = lane_role(); o0 = r ? o : h; o1 = r ? h : o; }
+};
+TCB_D Fp fp_select(bool c, const Fp &a, const Fp &b) {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+TCB_D Fp2S operator+(const Fp2S &a, const Fp2S &b) { Fp2S r; r.h = a.h + b.h; return r; }
+TCB_D Fp2S operator-(const Fp2S &a, const Fp2S &b) { Fp2S r; r.h = a.h - b.h; return r; }
+TCB_D Fp2S operator-(const Fp2S &a) { Fp2S r; r.h = -a.h; return r; }
+TCB_D Fp2S dbl(const Fp2S &a) { Fp2S r; r.h = dbl(a.h); return r; }
+TCB_D Fp2S conj(const Fp2S &a) { Fp2S r; r.h = lane_role() ? -a.h : a.h; return r; }
+TCB_D Fp2S operator*(const Fp2S &a, const Fp2S &b) {
+    Fp oa = partner(a.h), ob = partner(b.h);
+    bool role = lane_role();
+    // role 0: a0*b0 + a1*(-b1) = h_a*h_b + o_a*(-o_b);  role 1: a0*b1 + a1*b0 = o_a*h_b + h_a*o_b
+    Fp y1 = fp_select(role, ob, b.h);
+    Fp y2 = fp_select(role, b.h, -ob);
+    Fp2S r; r.h = dot2(a.h, y1, oa, y2);
+    return r;
+}
+TCB_D Fp2S sqr(const Fp2S &a) {
+    Fp o = partner(a.h);
+    bool role = lane_role();
+    // role 0: (a0 + a1)(a0 - a1);  role 1: (2 a0) a1
+    Fp x = fp_select(role, dbl(o), a.h + o);
+    Fp y = fp_select(role, a.h, a.h - o);
+    Fp2S r; r.h = x * y;
+    return r;
+}
+TCB_D Fp2S mul_fp(const Fp2S &a, const Fp &k) { Fp2S r; r.h = a.h * k; return r; }
+TCB_D Fp2S mul_xi(const Fp2S &a) {
+    Fp o = partner(a.h);
+    Fp2S r; r.h = a.h + fp_select(lane_role(), o, -o);   // role 0: c0 - c1; role 1: c1 + c0
+    return r;
+}
+TCB_D bool is_zero(const Fp2S &a) { return pair_and(a.h.is_zero()); }
+TCB_D bool eq(const Fp2S &a, const Fp2S &b) { return pair_and(a.h == b.h); }
+TCB_D Fp2S select(bool c, const Fp2S &a, const Fp2S &b) { Fp2S r; r.h = fp_select(c, a.h, b.h); return r; }
+TCB_D Fp norm(const Fp2S &a) { Fp s = sqr(a.h); return s + partner(s); }
+TCB_D Fp2S inv(const Fp2S &a) {
+    Fp n = fp_inv(norm(a));
+    Fp t = a.h * n;
+    Fp2S r; r.h = lane_role() ? -t : t;
+    return r;
+}
+#endif
+
+// canonical ordering of EXTERNAL pairing Fq2: by c1 then c0 (A3). Works for both engines.
+template <class F2>
+TCB_HD int fp2_cmp(const F2 &a, const F2 &b) {
+    Fp a0, a1, b0, b1;
+    a.gather(a0, a1);
+    b.gather(b0, b1);
+    int c = fp_cmp(a1, b1);
+    return c ? c : fp_cmp(a0, b0);
+}
+
+template <class F2, class E>
+TCB_HDN F2 fp2_pow(const F2 &a) {
+    F2 acc = F2::one();
+    bool started = false;
+    for (int i = E::N * 32 - 1; i >= 0; i--) {
+        if (started) acc = sqr(acc);
+        if ((E::get(i >> 5) >> (i & 31)) & 1) {
+            if (started) acc = acc * a; else { acc = a; started = true; }
+        }
+    }
+    return acc;
+}
+// Algorithm 9 of eprint 2012/685; returns false when `a` is a non-residue.
+template <class F2>
+TCB_HD bool fp2_sqrt(F2 &out, const F2 &a) {
+    if (is_zero(a)) { out = F2::zero(); return true; }
+    F2 a1 = fp2_pow<F2, ExpPm3d4>(a);
+    F2 alpha = sqr(a1) * a;
+    F2 a0 = conj(alpha) * alpha;
+    F2 neg1 = -F2::one();
+    if (eq(a0, neg1)) return false;
+    a1 = a1 * a;
+    if (eq(alpha, neg1)) {
+        a1 = a1 * F2::from_halves(Fp::zero(), fp_one());
+    } else {
+        alpha = fp2_pow<F2, ExpPm1d2>(alpha + F2::one());
+        a1 = a1 * alpha;
+    }
+    out = a1;
+    return true;
+}
+
+// ----------------------------------------------------------------------------- Fp6 = Fp2[v]/(v^3 - xi)
+template <class F2>
+struct Fp6T { F2 c0, c1, c2; };
+template <class F2> TCB_HD Fp6T<F2> operator+(const Fp6T<F2> &a, const Fp6T<F2> &b) { Fp6T<F2> r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; r.c2 = a.c2 + b.c2; return r; }
+template <class F2> TCB_HD Fp6T<F2> operator-(const Fp6T<F2> &a, const Fp6T<F2> &b) { Fp6T<F2> r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; r.c2 = a.c2 - b.c2; return r; }
+template <class F2> TCB_HD Fp6T<F2> operator-(const Fp6T<F2> &a) { Fp6T<F2> r; r.c0 = -a.c0; r.c1 = -a.c1; r.c2 = -a.c2; return r; }
+template <class F2> TCB_HD Fp6T<F2> mul_v(const Fp6T<F2> &a) { Fp6T<F2> r; r.c0 = mul_xi(a.c2); r.c1 = a.c0; r.c2 = a.c1; return r; }
+template <class F2>
+TCB_HDN Fp6T<F2> fp6_mul(const Fp6T<F2> &a, const Fp6T<F2> &b) {
+    F2 v0 = a.c0 * b.c0, v1 = a.c1 * b.c1, v2 = a.c2 * b.c2;
+    Fp6T<F2> r;
+    r.c0 = mul_xi((a.c1 + a.c2) * (b.c1 + b.c2) - v1 - v2) + v0;
+    r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - v0 - v1 + mul_xi(v2);
+    r.c2 = (a.c0 + a.c2) * (b.c0 + b.c2) - v0 - v2 + v1;
+    return r;
+}
+template <class F2>
+TCB_HDN Fp6T<F2> fp6_sqr(const Fp6T<F2> &a) {   // CH-SQR2
+    F2 s0 = sqr(a.c0);
+    F2 ab = a.c0 * a.c1;
+    F2 s1 = dbl(ab);
+    F2 s2 = sqr(a.c0 - a.c1 + a.c2);
+    F2 bc = a.c1 * a.c2;
+    F2 s3 = dbl(bc);
+    F2 s4 = sqr(a.c2);
+    Fp6T<F2> r;
+    r.c0 = s0 + mul_xi(s3);
+    r.c1 = s1 + mul_xi(s4);
+    r.c2 = s1 + s2 + s3 - s0 - s4;
+    return r;
+}
+// a * (b1 v)
+template <class F2>
+TCB_HD Fp6T<F2> fp6_mul_by_1(const Fp6T<F2> &a, const F2 &b1) {
+    Fp6T<F2> r;
+    r.c0 = mul_xi(a.c2 * b1);
+    r.c1 = a.c0 * b1;
+    r.c2 = a.c1 * b1;
+    return r;
+}
+// a * (b0 + b1 v)
+template <class F2>
+TCB_HD Fp6T<F2> fp6_mul_by_01(const Fp6T<F2> &a, const F2 &b0, const F2 &b1) {
+    F2 v0 = a.c0 * b0, v1 = a.c1 * b1;
+    Fp6T<F2> r;
+    r.c0 = mul_xi((a.c1 + a.c2) * b1 - v1) + v0;
+    r.c1 = (a.c0 + a.c1) * (b0 + b1) - v0 - v1;
+    r.c2 = (a.c0 + a.c2) * b0 - v0 + v1;
+    return r;
+}
+template <class F2>
+TCB_HDN Fp6T<F2> fp6_inv(const Fp6T<F2> &a) {
+    F2 t0 = sqr(a.c0) - mul_xi(a.c1 * a.c2);
+    F2 t1 = mul_xi(sqr(a.c2)) - a.c0 * a.c1;
+    F2 t2 = sqr(a.c1) - a.c0 * a.c2;
+    F2 d = inv(mul_xi(a.c2 * t1 + a.c1 * t2) + a.c0 * t0);
+    Fp6T<F2> r;
+    r.c0 = t0 * d; r.c1 = t1 * d; r.c2 = t2 * d;
+    return r;
+}
+
+// ----------------------------------------------------------------------------- Fp12 = Fp6[w]/(w^2 - v)
+template <class F2>
+struct Fp12T { Fp6T<F2> c0, c1; };
+template <class F2>
+TCB_HD Fp12T<F2> fp12_one() {
+    Fp12T<F2> r;
+    r.c0.c0 = F2::one(); r.c0.c1 = F2::zero(); r.c0.c2 = F2::zero();
+    r.c1.c0 = F2::zero(); r.c1.c1 = F2::zero(); r.c1.c2 = F2::zero();
+    return r;
+}
+template <class F2>
+TCB_HDN Fp12T<F2> fp12_mul(const Fp12T<F2> &a, const Fp12T<F2> &b) {
+    Fp6T<F2> aa = fp6_mul(a.c0, b.c0);
+    Fp6T<F2> bb = fp6_mul(a.c1, b.c1);
+    Fp12T<F2> r;
+    r.c1 = fp6_mul(a.c0 + a.c1, b.c0 + b.c1) - aa - bb;
+    r.c0 = aa + mul_v(bb);
+    return r;
+}
+template <class F2>
+TCB_HDN Fp12T<F2> fp12_sqr(const Fp12T<F2> &a) {
+    Fp6T<F2> ab = fp6_mul(a.c0, a.c1);
+    Fp12T<F2> r;
+    r.c0 = fp6_mul(a.c0 + a.c1, a.c0 + mul_v(a.c1)) - ab - mul_v(ab);
+    r.c1 = ab + ab;
+    return r;
+}
+template <class F2> TCB_HD Fp12T<F2> fp12_conj(const Fp12T<F2> &a) { Fp12T<F2> r; r.c0 = a.c0; r.c1 = -a.c1; return r; }
+template <class F2>
+TCB_HDN Fp12T<F2> fp12_inv(const Fp12T<F2> &a) {
+    Fp6T<F2> t = fp6_inv(fp6_sqr(a.c0) - mul_v(fp6_sqr(a.c1)));
+    Fp12T<F2> r;
+    r.c0 = fp6_mul(a.c0, t);
+    r.c1 = -fp6_mul(a.c1, t);
+    return r;
+}
+// Frobenius p^k: the coefficient of v^i w^j (w-degree m = 2i + j) is conjugated k times and
+// multiplied by frob[k][m].
+template <class F2>
+TCB_HDN Fp12T<F2> fp12_frob(const Fp12T<F2> &a, int k) {
+    const Consts &C = CONSTS();
+    Fp12T<F2> r;
+    bool odd = k & 1;
+    r.c0.c0 = odd ? conj(a.c0.c0) : a.c0.c0;
+    r.c1.c0 = (odd ? conj(a.c1.c0) : a.c1.c0) * F2::load(C.frob[k][1]);
+    r.c0.c1 = (odd ? conj(a.c0.c1) : a.c0.c1) * F2::load(C.frob[k][2]);
+    r.c1.c1 = (odd ? conj(a.c1.c1) : a.c1.c1) * F2::load(C.frob[k][3]);
+    r.c0.c2 = (odd ? conj(a.c0.c2) : a.c0.c2) * F2::load(C.frob[k][4]);
+    r.c1.c2 = (odd ? conj(a.c1.c2) : a.c1.c2) * F2::load(C.frob[k][5]);
+    return r;
+}
+// f * (l0 + l1 v + l4 v w)   — the sparse line element of the M-type twist
+template <class F2>
+TCB_HDN void fp12_mul_by_014(Fp12T<F2> &f, const F2 &l0, const F2 &l1, const F2 &l4) {
+    Fp6T<F2> aa = fp6_mul_by_01(f.c0, l0, l1);
+    Fp6T<F2> bb = fp6_mul_by_1(f.c1, l4);
+    Fp6T<F2> s = fp6_mul_by_01(f.c0 + f.c1, l0, l1 + l4);
+    f.c1 = s - aa - bb;
+    f.c0 = mul_v(bb) + aa;
+}
+template <class F2>
+TCB_HD bool fp12_is_one(const Fp12T<F2> &a) {
+    bool z = is_zero(a.c0.c1);
+    z = is_zero(a.c0.c2) && z;
+    z = is_zero(a.c1.c0) && z;
+    z = is_zero(a.c1.c1) && z;
+    z = is_zero(a.c1.c2) && z;
+    z = eq(a.c0.c0, F2::one()) && z;
+    return z;
+}
+// Granger-Scott squaring, valid in the cyclotomic subgroup (after the easy part)
+template <class F2>
+TCB_HD void fp4_sqr(F2 &c0, F2 &c1, const F2 &a, const F2 &b) {
+    F2 t0 = sqr(a), t1 = sqr(b);
+    c0 = mul_xi(t1) + t0;
+    c1 = sqr(a + b) - t0 - t1;
+}
+template <class F2>
+TCB_HDN Fp12T<F2> fp12_cyclo_sqr(const Fp12T<F2> &f) {
+    F2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+    F2 t0, t1, t2, t3;
+    fp4_sqr(t0, t1, z0, z1);
+    z0 = t0 - z0; z0 = z0 + z0 + t0;
+    z1 = t1 + z1; z1 = z1 + z1 + t1;
+    fp4_sqr(t0, t1, z2, z3);
+    fp4_sqr(t2, t3, z4, z5);
+    z4 = t0 - z4; z4 = z4 + z4 + t0;
+    z5 = t1 + z5; z5 = z5 + z5 + t1;
+    t0 = mul_xi(t3);
+    z2 = t0 + z2; z2 = z2 + z2 + t0;
+    z3 = t2 - z3; z3 = z3 + z3 + t2;
+    Fp12T<F2> r;
+    r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
+    r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
+    return r;
+}
+// f^|x| then conjugate (x < 0), for f in the cyclotomic subgroup
+template <class F2>
+TCB_HDN Fp12T<F2> fp12_exp_by_x(const Fp12T<F2> &f, u64 x) {
+    Fp12T<F2> acc = f;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    for (int i = top - 1; i >= 0; i--) {
+        acc = fp12_cyclo_sqr(acc);
+        if ((x >> i) & 1) acc = fp12_mul(acc, f);
+    }
+    return fp12_conj(acc);
+}
+// f^(3 (p^12 - 1)/r): easy part, then the hard part by the x-chain (same chain as EXTERNAL
+// pairing 0.16 final_exponentiation, with cyclotomic squarings).  Only == 1 is ever observed.
+template <class F2>
+TCB_HDN Fp12T<F2> final_exponentiation(const Fp12T<F2> &in) {
+    Fp12T<F2> f2 = fp12_inv(in);
+    Fp12T<F2> r = fp12_mul(fp12_conj(in), f2);
+    f2 = r;
+    r = fp12_mul(fp12_frob(r, 2), f2);
+    const u64 x = TCB_BLS_X;
+    Fp12T<F2> y0 = fp12_cyclo_sqr(r);
+    Fp12T<F2> y1 = fp12_exp_by_x(y0, x);
+    Fp12T<F2> y2 = fp12_exp_by_x(y1, x >> 1);
+    Fp12T<F2> y3 = fp12_conj(r);
+    y1 = fp12_mul(y1, y3);
+    y1 = fp12_conj(y1);
+    y1 = fp12_mul(y1, y2);
+    y2 = fp12_exp_by_x(y1, x);
+    y3 = fp12_exp_by_x(y2, x);
+    y1 = fp12_conj(y1);
+    y3 = fp12_mul(y3, y1);
+    y1 = fp12_conj(y1);
+    y1 = fp12_frob(y1, 3);
+    y2 = fp12_frob(y2, 2);
+    y1 = fp12_mul(y1, y2);
+    y2 = fp12_exp_by_x(y3, x);
+    y2 = fp12_mul(y2, y0);
+    y2 = fp12_mul(y2, r);
+    y1 = fp12_mul(y1, y2);
+    y2 = fp12_frob(y3, 1);
+    return fp12_mul(y1, y2);
+}
+
+// ----------------------------------------------------------------------------- curves (Jacobian), F = Fp (G1) or F2 (G2)
+TCB_HD bool is_zero(const Fp &a) { return a.is_zero(); }
+TCB_HD bool eq(const Fp &a, const Fp &b) { return a == b; }
+TCB_HD Fp inv(const Fp &a) { return fp_inv(a); }
+TCB_HD Fp select(bool c, const Fp &a, const Fp &b) { return c ? a : b; }
+template <class F> struct FieldOne;
+template <> struct FieldOne<Fp> { TCB_HD static Fp one() { return fp_one(); } TCB_HD static Fp zero() { return Fp::zero(); } };
+template <> struct FieldOne<Fp2> { TCB_HD static Fp2 one() { return Fp2::one(); } TCB_HD static Fp2 zero() { return Fp2::zero(); } };
+#if defined(__CUDACC__)
+template <> struct FieldOne<Fp2S> { TCB_D static Fp2S one() { return Fp2S::one(); } TCB_D static Fp2S zero() { return Fp2S::zero(); } };
+#endif
+
+template <class F> struct Aff { F x, y; bool inf; };
+template <class F> struct Jac { F x, y, z; };   // z == 0 <=> infinity
+
+template <class F> TCB_HD Jac<F> jac_inf() { Jac<F> r; r.x = FieldOne<F>::zero(); r.y = FieldOne<F>::one(); r.z = FieldOne<F>::zero(); return r; }
+template <class F> TCB_HD bool jac_is_inf(const Jac<F> &p) { return is_zero(p.z); }
+template <class F> TCB_HD Jac<F> jac_from_aff(const Aff<F> &a) {
+    Jac<F> r;
+    if (a.inf) return jac_inf<F>();
+    r.x = a.x; r.y = a.y; r.z = FieldOne<F>::one();
+    return r;
+}
+template <class F> TCB_HD Jac<F> jac_neg(const Jac<F> &p) { Jac<F> r = p; r.y = -p.y; return r; }
+template <class F>
+TCB_HDN Aff<F> jac_to_aff(const Jac<F> &p) {
+    Aff<F> r;
+    if (jac_is_inf(p)) { r.inf = true; r.x = FieldOne<F>::zero(); r.y = FieldOne<F>::zero(); return r; }
+    F zi = inv(p.z), zi2 = sqr(zi);
+    r.x = p.x * zi2; r.y = p.y * (zi2 * zi); r.inf = false;
+    return r;
+}
+template <class F>
+TCB_HDN Jac<F> jac_dbl(const Jac<F> &p) {   // dbl-2009-l (a = 0); also correct for infinity (z stays 0)
+    F a = sqr(p.x), b = sqr(p.y), c = sqr(b);
+    F d = dbl(sqr(p.x + b) - a - c);
+    F e = dbl(a) + a;
+    F f = sqr(e);
+    Jac<F> r;
+    r.z = dbl(p.y * p.z);
+    r.x = f - dbl(d);
+    r.y = e * (d - r.x) - dbl(dbl(dbl(c)));
+    return r;
+}
+template <class F>
+TCB_HDN Jac<F> jac_add_mixed(const Jac<F> &p, const Aff<F> &q) {   // madd-2007-bl + exceptional cases
+    if (q.inf) return p;
+    if (jac_is_inf(p)) return jac_from_aff(q);
+    F z1z1 = sqr(p.z);
+    F u2 = q.x * z1z1;
+    F s2 = q.y * p.z * z1z1;
+    if (eq(p.x, u2)) {
+        if (eq(p.y, s2)) return jac_dbl(p);
+        return jac_inf<F>();
+    }
+    F h = u2 - p.x, hh = sqr(h);
+    F i = dbl(dbl(hh));
+    F j = h * i;
+    F rr = dbl(s2 - p.y);
+    F v = p.x * i;
+    Jac<F> r;
+    r.x = sqr(rr) - j - dbl(v);
+    r.y = rr * (v - r.x) - dbl(p.y * j);
+    r.z = sqr(p.z + h) - z1z1 - hh;
+    return r;
+}
+template <class F>
+TCB_HDN Jac<F> jac_add(const Jac<F> &p, const Jac<F> &q) {   // add-2007-bl + exceptional cases
+    if (jac_is_inf(p)) return q;
+    if (jac_is_inf(q)) return p;
+    F z1z1 = sqr(p.z), z2z2 = sqr(q.z);
+    F u1 = p.x * z2z2, u2 = q.x * z1z1;
+    F s1 = p.y * q.z * z2z2, s2 = q.y * p.z * z1z1;
+    if (eq(u1, u2)) {
+        if (eq(s1, s2)) return jac_dbl(p);
+        return jac_inf<F>();
+    }
+    F h = u2 - u1;
+    F i = sqr(dbl(h));
+    F j = h * i;
+    F rr = dbl(s2 - s1);
+    F v = u1 * i;
+    Jac<F> r;
+    r.x = sqr(rr) - j - dbl(v);
+    r.y = rr * (v - r.x) - dbl(s1 * j);
+    r.z = (sqr(p.z + q.z) - z1z1 - z2z2) * h;
+    return r;
+}
+// k * P for an affine base, k given as NL little-endian u32 limbs (canonical integer).
+// MSB-first double-and-add; the group element is unique whatever the algorithm (App. A).
+template <class F, int NL>
+TCB_HDN Jac<F> jac_mul_aff(const Aff<F> &p, const u32 *k) {
+    Jac<F> acc = jac_inf<F>();
+    bool started = false;
+    for (int i = NL * 32 - 1; i >= 0; i--) {
+        if (started) acc = jac_dbl(acc);
+        if ((k[i >> 5] >> (i & 31)) & 1) { acc = jac_add_mixed(acc, p); started = true; }
+    }
+    return acc;
+}
+template <class F, class E>
+TCB_HDN Jac<F> jac_mul_const(const Aff<F> &p) {
+    Jac<F> acc = jac_inf<F>();
+    bool started = false;
+    for (int i = E::N * 32 - 1; i >= 0; i--) {
+        if (started) acc = jac_dbl(acc);
+        if ((E::get(i >> 5) >> (i & 31)) & 1) { acc = jac_add_mixed(acc, p); started = true; }
+    }
+    return acc;
+}
+// k * P for a Jacobian base (Commitment::evaluate's `result.mul_assign(x)`)
+template <class F, int NL>
+TCB_HDN Jac<F> jac_mul_jac(const Jac<F> &p, const u32 *k) {
+    Jac<F> acc = jac_inf<F>();
+    bool started = false;
+    for (int i = NL * 32 - 1; i >= 0; i--) {
+        if (started) acc = jac_dbl(acc);
+        if ((k[i >> 5] >> (i & 31)) & 1) { acc = started ? jac_add(acc, p) : p; started = true; }
+    }
+    return acc;
+}
+
+// ----------------------------------------------------------------------------- Miller loop (M-type twist, projective lines)
+template <class F2> struct Line { F2 a, b, c; };
+template <class F2>
+TCB_HDN Line<F2> doubling_step(Jac<F2> &r) {
+    F2 t0 = sqr(r.x), t1 = sqr(r.y), t2 = sqr(t1);
+    F2 t3 = dbl(sqr(t1 + r.x) - t0 - t2);
+    F2 t4 = dbl(t0) + t0;
+    F2 t6 = r.x + t4;
+    F2 t5 = sqr(t4);
+    F2 zsq = sqr(r.z);
+    r.x = t5 - dbl(t3);
+    r.z = sqr(r.z + r.y) - t1 - zsq;
+    r.y = (t3 - r.x) * t4 - dbl(dbl(dbl(t2)));
+    Line<F2> l;
+    l.b = -dbl(t4 * zsq);
+    l.c = sqr(t6) - t0 - t5 - dbl(dbl(t1));
+    l.a = dbl(r.z * zsq);
+    return l;
+}
+template <class F2>
+TCB_HDN Line<F2> addition_step(Jac<F2> &r, const Aff<F2> &q) {
+    F2 zsq = sqr(r.z), ysq = sqr(q.y);
+    F2 t0 = zsq * q.x;
+    F2 t1 = (sqr(q.y + r.z) - ysq - zsq) * zsq;
+    F2 t2 = t0 - r.x;
+    F2 t3 = sqr(t2);
+    F2 t4 = dbl(dbl(t3));
+    F2 t5 = t4 * t2;
+    F2 t6 = t1 - dbl(r.y);
+    F2 t9 = t6 * q.x;
+    F2 t7 = t4 * r.x;
+    r.x = sqr(t6) - t5 - dbl(t7);
+    r.z = sqr(r.z + t2) - zsq - t3;
+    F2 t10 = q.y + r.z;
+    F2 t8 = (t7 - r.x) * t6;
+    r.y = t8 - dbl(r.y * t5);
+    t10 = sqr(t10) - ysq - sqr(r.z);
+    Line<F2> l;
+    l.c = dbl(t9) - t10;
+    l.a = dbl(r.z);
+    l.b = dbl(-t6);
+    return l;
+}
+template <class F2>
+TCB_HD void ell(Fp12T<F2> &f, const Line<F2> &l, const Aff<Fp> &p) {
+    fp12_mul_by_014(f, l.c, mul_fp(l.b, p.x), mul_fp(l.a, p.y));
+}
+// Product of up to two Miller loops with one shared accumulator.  A pair with an infinity
+// operand contributes 1 (A8).
+template <class F2>
+TCB_HDN Fp12T<F2> miller_loop2(const Aff<Fp> &p0, const Aff<F2> &q0, const Aff<Fp> &p1, const Aff<F2> &q1) {
+    Fp12T<F2> f = fp12_one<F2>();
+    bool act0 = !(p0.inf || q0.inf), act1 = !(p1.inf || q1.inf);
+    Jac<F2> r0 = jac_from_aff(q0), r1 = jac_from_aff(q1);
+    const u64 xs = TCB_BLS_X >> 1;
+    for (int i = 61; i >= 0; i--) {   // bit 62 is the leading one of x >> 1
+        bool bit = (xs >> i) & 1;
+        if (act0) { Line<F2> l = doubling_step(r0); ell(f, l, p0); }
+        if (act1) { Line<F2> l = doubling_step(r1); ell(f, l, p1); }
+        if (bit) {
+            if (act0) { Line<F2> l = addition_step(r0, q0); ell(f, l, p0); }
+            if (act1) { Line<F2> l = addition_step(r1, q1); ell(f, l, p1); }
+        }
+        f = fp12_sqr(f);
+    }
+    if (act0) { Line<F2> l = doubling_step(r0); ell(f, l, p0); }
+    if (act1) { Line<F2> l = doubling_step(r1); ell(f, l, p1); }
+    return fp12_conj(f);
+}
+// e(a,b) == e(c,d)
+template <class F2>
+TCB_HD bool pairing_eq(const Aff<Fp> &a, const Aff<F2> &b, const Aff<Fp> &c, const Aff<F2> &d) {
+    Aff<Fp> nc = c;
+    nc.y = -c.y;
+    Fp12T<F2> f = miller_loop2(a, b, nc, d);
+    return fp12_is_one(final_exponentiation(f));
+}
+
+}  // namespace tcb
