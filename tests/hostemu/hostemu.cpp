@@ -92,3 +92,5 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff,
     for (size_t i = 0; i < n; i++) task_commit_eval(i, deg, tab.data(), x, out);
     return 0;
 }
+
+extern "C" uint64_t tcb_emu_mac_count(int reset) { uint64_t v = g_mac_count; if (reset) g_mac_count = 0; return v; }

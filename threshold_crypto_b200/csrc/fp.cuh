@@ -64,6 +64,7 @@ TCB_D void subc(u32 &d, u32 a, u32 b) { TCB_ASM("subc.u32 %0, %1, %2;" : "=r"(d)
 #else
 // Bit-exact host emulation of the PTX carry flag (test infrastructure for tests/hostemu).
 static thread_local u32 g_cc;
+static thread_local u64 g_mac_count;   // algorithmic 32x32->64 MACs issued by mont_mul_impl (host only)
 inline void mul_wide_pair(u32 &lo, u32 &hi, u32 a, u32 b) { u64 p = (u64)a * b; lo = (u32)p; hi = (u32)(p >> 32); }
 inline void mad_pair_cc(u32 &lo, u32 &hi, u32 a, u32 b) {
     u64 p = (u64)a * b;
@@ -222,6 +223,9 @@ template <class P, bool DOT2>
 TCB_HD Mont<P> mont_mul_impl(const Mont<P> &a, const Mont<P> &b, const Mont<P> &c, const Mont<P> &d) {
     constexpr int N = P::N;
     static_assert(N % 2 == 0, "even limb count");
+#if !defined(__CUDA_ARCH__)
+    g_mac_count += (DOT2 ? 3 : 2) * N * N + N;   // product rows + reduction rows + the N m_i multiplies
+#endif
     u32 even[N], odd[N];
     // the high limb above a[N-1] used by a+1 views is never read: views use indices j+1 <= N-1 for j even <= N-2
     mad_row_redc<P, true, DOT2>(even, odd, a.l, b.l[0], c.l, d.l[0]);

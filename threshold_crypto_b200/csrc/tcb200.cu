@@ -148,6 +148,33 @@ __global__ void k_selftest_fp(size_t n, u64 seed, unsigned long long *bad) {
         Fp t0 = mont_mul_portable<FpParams>(x.c0, y.c0) - mont_mul_portable<FpParams>(x.c1, y.c1);
         Fp t1 = mont_mul_portable<FpParams>(x.c0, y.c1) + mont_mul_portable<FpParams>(x.c1, y.c0);
         if (pm.c0 != t0 || pm.c1 != t1) errs++;
+        // predicates and rarely-used ops of the sliced engine against the scalar one
+        Fp2 z0 = x; z0.c1 = Fp::zero();          // only one half zero: exercises pair_and
+        Fp2S z0s = Fp2S::from_halves(z0.c0, z0.c1);
+        if (is_zero(z0s) != is_zero(z0)) errs++;
+        if (is_zero(Fp2S::zero()) != true) errs++;
+        if (eq(xs, ys) != eq(x, y) || !eq(xs, xs)) errs++;
+        if (eq(z0s, xs) != eq(z0, x)) errs++;
+        Fp2 pc = conj(x), pi = inv(x), pn = -x, pf = mul_fp(x, c);
+        Fp2S qc = conj(xs), qi = inv(xs), qn = -xs, qf = mul_fp(xs, c);
+        if (qc.h != (role ? pc.c1 : pc.c0)) errs++;
+        if (qi.h != (role ? pi.c1 : pi.c0)) errs++;
+        if (qn.h != (role ? pn.c1 : pn.c0)) errs++;
+        if (qf.h != (role ? pf.c1 : pf.c0)) errs++;
+        if (fp2_cmp(xs, ys) != fp2_cmp(x, y)) errs++;
+        if (norm(xs) != norm(x)) errs++;
+        Fp2 one_s; Fp2S::one().gather(one_s.c0, one_s.c1);
+        if (!eq(one_s, Fp2::one())) errs++;
+        if (((i >> 1) & 31) == 0) {   // a few square roots (expensive); the condition is pair-uniform
+            Fp2 sq = sqr(x), r1;
+            Fp2S r2;
+            bool ok1 = fp2_sqrt(r1, sq), ok2 = fp2_sqrt(r2, Fp2S::from_halves(sq.c0, sq.c1));
+            if (!ok1 || !ok2) errs++;
+            if (r2.h != (role ? r1.c1 : r1.c0)) errs++;
+            Fp2 nr;
+            bool ok3 = fp2_sqrt(nr, x), ok4 = fp2_sqrt(r2, xs);
+            if (ok3 != ok4) errs++;
+        }
     }
     if (errs) atomicAdd(bad, (unsigned long long)errs);
 }

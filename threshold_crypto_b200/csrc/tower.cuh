@@ -95,7 +95,8 @@ TCB_D Fp partner(const Fp &a) {
     for (int i = 0; i < 12; i++) r.l[i] = __shfl_xor_sync(m, a.l[i], 1);
     return r;
 }
-TCB_D bool pair_and(bool v) { u32 m = pair_mask(); return v && __shfl_xor_sync(m, (int)v, 1); }
+// NB: the shuffle must be executed by BOTH lanes unconditionally (no short-circuit)
+TCB_D bool pair_and(bool v) { u32 m = pair_mask(); int o = __shfl_xor_sync(m, (int)v, 1); return v & (o != 0); }
 #endif
 
 // ----------------------------------------------------------------------------- Fp2, one element per thread
