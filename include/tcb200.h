@@ -38,8 +38,9 @@ extern "C" {
 typedef struct tcb_ctx tcb_ctx;
 
 /* Engine variants for the G2 / pairing kernels (tcb_set_engine): */
-#define TCB_ENGINE_PAIR 0   /* one item per lane pair, Fp2 sliced across the pair (default) */
+#define TCB_ENGINE_PAIR 0   /* one item per lane pair, Fp2 sliced across the pair */
 #define TCB_ENGINE_THREAD 1 /* one item per thread */
+#define TCB_ENGINE_QUAD 2   /* default: pairing checks on lane quads (register-resident Fp12), the rest on lane pairs */
 
 int tcb_init(tcb_ctx **ctx, const int *device_ids, int n_devices);
 void tcb_free(tcb_ctx *ctx);

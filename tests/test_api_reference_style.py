@@ -1,0 +1,85 @@
+"""The reference's own scheme tests (src/lib.rs:790-940, src/poly.rs:783-797), re-expressed on the
+Python mirror of its API (threshold_crypto_b200/api.py).  On the CPU box they run on the
+host-emulation build of the device code (logic check); on the B200 they run on the CUDA library."""
+import numpy as np
+import pytest
+
+from threshold_crypto_b200 import api
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def tc(request):
+    if request.param == "emu":
+        api.set_engine(request.getfixturevalue("emu"))
+    else:
+        api.set_engine(request.getfixturevalue("gpu_engine"))
+    yield api
+    api.set_engine(None)
+
+
+def rng():
+    return np.random.default_rng(20260925)
+
+
+def test_simple_sig(tc):                      # src/lib.rs:811-820
+    r = rng()
+    sk0, sk1 = tc.SecretKey(int.from_bytes(r.bytes(40), "little")), tc.SecretKey(int.from_bytes(r.bytes(40), "little"))
+    pk0 = sk0.public_key()
+    msg0, msg1 = b"Real news", b"Fake news"
+    assert pk0.verify(sk0.sign(msg0), msg0)
+    assert not pk0.verify(sk1.sign(msg0), msg0)     # wrong key
+    assert not pk0.verify(sk0.sign(msg1), msg0)     # wrong message
+
+
+def test_threshold_sig(tc):                   # src/lib.rs:823-873
+    sk_set = tc.SecretKeySet.random(3, rng())
+    pk_set = sk_set.public_keys()
+    pk_master = pk_set.public_key()
+    assert pk_master != pk_set.public_key_share(0)
+    assert pk_master == sk_set.secret_key().public_key()
+    msg = b"Totally real news"
+    sigs = {i: sk_set.secret_key_share(i).sign(msg) for i in (5, 8, 7, 10)}
+    for i, s in sigs.items():
+        assert pk_set.public_key_share(i).verify(s, msg)
+    sig = pk_set.combine_signatures(sigs)
+    assert pk_set.public_key().verify(sig, msg)
+    sigs2 = {i: sk_set.secret_key_share(i).sign(msg) for i in (42, 43, 44, 45)}
+    sig2 = pk_set.combine_signatures(sigs2)
+    assert sig == sig2                               # two disjoint share sets give the SAME signature
+    with pytest.raises(tc.NotEnoughShares):
+        pk_set.combine_signatures({5: sigs[5], 8: sigs[8], 7: sigs[7]})
+
+
+def test_interpolate_equals_evaluate_at_zero(tc):   # src/lib.rs:794-808
+    r = rng()
+    for deg in range(0, 4):
+        poly = tc.Poly.random(deg, r)
+        comm = poly.commitment()
+        x, vals = 0, []
+        for _ in range(deg + 1):
+            x += int(r.integers(1, 5))
+            vals.append((x - 1, tc.DecryptionShare(comm.evaluate(x))))
+        # interpolate over G1 == comm.evaluate(0); go through PublicKeySet.decrypt's machinery with an empty body
+        pts = np.stack([v.raw for _, v in vals])
+        xs = tc._frs([tc.into_fr_plus_1(i) for i, _ in vals])
+        out, st = tc.engine().combine_g1_batch(1, deg, xs, pts)
+        assert not st.any() and np.array_equal(out[0], comm.evaluate(0))
+
+
+def test_threshold_enc_decrypt_roundtrip(tc, O):     # src/lib.rs:908-939 (encrypt done by the oracle: next-row item)
+    sk_set = tc.SecretKeySet.random(2, rng())
+    pk_set = sk_set.public_keys()
+    msg = b"Totally real news"
+    r32 = tc._fr(0x1234567890abcdef1234567890abcdef)
+    u, v, w = O.encrypt(pk_set.public_key().raw, r32, msg)
+    ct = tc.Ciphertext(u, v, w)
+    shares = {i: sk_set.secret_key_share(i).decrypt_share_no_verify(ct) for i in (8, 5, 9)}
+    assert pk_set.decrypt(shares, ct) == msg
+    with pytest.raises(tc.NotEnoughShares):
+        pk_set.decrypt({8: shares[8], 5: shares[5]}, ct)
+
+
+def test_poly_kat(tc):                        # src/poly.rs:783-797: 5 X^3 + X - 2
+    poly = tc.Poly([-2, 1, 0, 5])
+    for x, y in ((-1, -8), (2, 40), (3, 136), (5, 628)):
+        assert poly.evaluate(x) == y % tc.R

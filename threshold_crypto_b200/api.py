@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference API for the hot path (names, argument meaning and error
+behaviour of /root/reference/src/lib.rs and src/poly.rs), backed by the C ABI of libtcb200.so.
+
+The reference's toolchain (Rust) is absent from this image, so this mirror is Python; the Rust
+binding a maintainer would write is in INTEGRATION.md.  Every arithmetic operation on curve
+points goes to the GPU through `Engine` (no CPU fallback); only the cheap Fr polynomial algebra
+(`Poly.evaluate`, index -> x = i + 1, `take(t+1)`, error mapping) stays on the host, exactly the
+split SURVEY.md §8b describes.  Single-item methods are batches of one; the `*_batch` functions
+are what a throughput-minded caller uses.
+"""
+import numpy as np
+
+from ._lib import Engine
+
+R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+PK_SIZE, SIG_SIZE = 48, 96          # compressed sizes (src/lib.rs:71,75); this mirror holds uncompressed bytes
+
+_engine = None
+
+
+def engine():
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+    return _engine
+
+
+def set_engine(e):
+    global _engine
+    _engine = e
+
+
+class Error(Exception):
+    """src/error.rs:7-20"""
+
+
+class NotEnoughShares(Error):
+    pass
+
+
+class DuplicateEntry(Error):
+    pass
+
+
+def into_fr(i):
+    """IntoFr (src/into_fr.rs:16-50): ints (negative ones negate), or an Fr given as int."""
+    return int(i) % R
+
+
+def into_fr_plus_1(i):   # src/lib.rs:769-773
+    return (into_fr(i) + 1) % R
+
+
+def _fr(v):
+    return np.frombuffer((int(v) % R).to_bytes(32, "little"), np.uint8)
+
+
+def _frs(vals):
+    return np.frombuffer(b"".join((int(v) % R).to_bytes(32, "little") for v in vals), np.uint8).copy()
+
+
+class _Point:
+    SIZE = 0
+
+    def __init__(self, raw):
+        raw = np.ascontiguousarray(raw, dtype=np.uint8).reshape(-1)
+        assert raw.size == self.SIZE
+        self.raw = raw
+
+    def __eq__(self, o):
+        return type(self) is type(o) and np.array_equal(self.raw, o.raw)
+
+    def __hash__(self):
+        return hash(self.raw.tobytes())
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self.raw.tobytes().hex()[:10]}..)"
+
+
+class Signature(_Point):      # Signature(G2), src/lib.rs:202
+    SIZE = 192
+
+
+class SignatureShare(Signature):   # src/lib.rs:266
+    pass
+
+
+class DecryptionShare(_Point):     # DecryptionShare(G1), src/lib.rs:517
+    SIZE = 96
+
+
+class PublicKey(_Point):           # PublicKey(G1), src/lib.rs:79
+    SIZE = 96
+
+    def verify_g2(self, sig, hash_g2_point):          # src/lib.rs:108-110
+        return bool(engine().verify_g2_batch(self.raw, np.asarray(hash_g2_point, np.uint8), None, sig.raw)[0])
+
+    def verify(self, sig, msg):                        # src/lib.rs:115-117
+        return bool(engine().verify_batch(self.raw, sig.raw, [bytes(msg)])[0])
+
+
+class PublicKeyShare(PublicKey):   # src/lib.rs:160
+
+    def verify_decryption_share(self, share, ct):      # src/lib.rs:182-186: e(share, H(U,V)) == e(pk_i, W)
+        raise NotImplementedError("needs hash_g1_g2 through the ABI (SURVEY §8f row 2)")
+
+
+class Ciphertext:                  # Ciphertext(G1, Vec<u8>, G2), src/lib.rs:474-478
+    def __init__(self, u, v, w):
+        self.u, self.v, self.w = np.asarray(u, np.uint8), bytes(v), np.asarray(w, np.uint8)
+
+
+class SecretKey:                   # SecretKey(Fr), src/lib.rs:302
+    def __init__(self, fr):
+        self.fr = int(fr) % R
+
+    def public_key(self):                              # src/lib.rs:367-369
+        return PublicKey(engine().g1_mul_gen_batch(_fr(self.fr))[0])
+
+    def sign_g2(self, hash_g2_point):                  # src/lib.rs:372-374
+        return Signature(engine().sign_g2_batch(_fr(self.fr), np.asarray(hash_g2_point, np.uint8))[0])
+
+    def sign(self, msg):                               # src/lib.rs:379-381
+        return Signature(engine().sign_batch(_fr(self.fr), [bytes(msg)])[0])
+
+    def __eq__(self, o):
+        return isinstance(o, SecretKey) and self.fr == o.fr
+
+    def __repr__(self):
+        return "SecretKey(...)"                        # Debug redaction, src/lib.rs:335-339
+
+
+class SecretKeyShare(SecretKey):   # src/lib.rs:412
+    def public_key_share(self):
+        return PublicKeyShare(self.public_key().raw)
+
+    def sign(self, msg):
+        return SignatureShare(super().sign(msg).raw)
+
+    def sign_g2(self, h):
+        return SignatureShare(super().sign_g2(h).raw)
+
+    def decrypt_share_no_verify(self, ct):             # src/lib.rs:460-462
+        return DecryptionShare(engine().decrypt_share_batch(_fr(self.fr), ct.u)[0])
+
+
+class Poly:                        # poly::Poly, src/poly.rs:40-44 (Fr algebra stays on the host)
+    def __init__(self, coeff):
+        self.coeff = [int(c) % R for c in coeff]
+
+    @staticmethod
+    def random(degree, rng):
+        return Poly([int.from_bytes(rng.bytes(40), "little") % R for _ in range(degree + 1)])
+
+    def degree(self):
+        return len(self.coeff) - 1
+
+    def evaluate(self, i):                             # src/poly.rs:358-369
+        x, acc = into_fr(i), 0
+        for c in reversed(self.coeff):
+            acc = (acc * x + c) % R
+        return acc
+
+    def commitment(self):                              # src/poly.rs:372-377: g1 * c_k on the GPU
+        return Commitment(engine().g1_mul_gen_batch(_frs(self.coeff)))
+
+
+class Commitment:                  # poly::Commitment, src/poly.rs:429-433
+    def __init__(self, coeff_g1):
+        self.coeff = np.ascontiguousarray(coeff_g1, dtype=np.uint8).reshape(-1, 96)
+
+    def degree(self):
+        return self.coeff.shape[0] - 1
+
+    def evaluate(self, i):                             # src/poly.rs:497-508
+        return self.evaluate_batch([i])[0]
+
+    def evaluate_batch(self, idx):
+        return engine().commitment_eval_batch(self.coeff, _frs([into_fr(i) for i in idx]))
+
+
+class SecretKeySet:                # src/lib.rs:630-688
+    def __init__(self, poly):
+        self.poly = poly
+
+    @staticmethod
+    def random(threshold, rng):
+        return SecretKeySet(Poly.random(threshold, rng))
+
+    def threshold(self):
+        return self.poly.degree()
+
+    def secret_key_share(self, i):                     # src/lib.rs:669-673
+        return SecretKeyShare(self.poly.evaluate(into_fr_plus_1(i)))
+
+    def public_keys(self):
+        return PublicKeySet(self.poly.commitment())
+
+    def secret_key(self):
+        return SecretKey(self.poly.evaluate(0))
+
+
+def _samples(t, shares):
+    """`take(t + 1)`, NotEnoughShares (src/lib.rs:726-733); shares: mapping or iterable of (i, share)."""
+    items = list(shares.items()) if hasattr(shares, "items") else list(shares)
+    items = items[: t + 1]
+    if len(items) <= t:
+        raise NotEnoughShares()
+    return items
+
+
+def _raise(status):
+    if status == 2:
+        raise DuplicateEntry()
+    if status:
+        raise Error(f"invalid encoding (status {status})")
+
+
+class PublicKeySet:                # src/lib.rs:539-626
+    def __init__(self, commit):
+        self.commit = commit
+
+    def threshold(self):
+        return self.commit.degree()
+
+    def public_key(self):
+        return PublicKey(self.commit.coeff[0])
+
+    def public_key_share(self, i):                     # src/lib.rs:570-573
+        return PublicKeyShare(self.commit.evaluate(into_fr_plus_1(i)))
+
+    def combine_signatures(self, shares):              # src/lib.rs:608-615
+        return combine_signatures_batch(self, [shares])[0]
+
+    def decrypt(self, shares, ct):                     # src/lib.rs:618-626
+        t = self.threshold()
+        items = _samples(t, shares)
+        xs = _frs([into_fr_plus_1(i) for i, _ in items])
+        pts = np.stack([s.raw for _, s in items])
+        out, st = engine().decrypt_batch(1, t, xs, pts, [ct.v])
+        _raise(int(st[0]))
+        return out[0]
+
+
+# ---- batched entry points (the reason this engine exists)
+def verify_batch(pks, sigs, msgs):
+    """[pk.verify(sig, msg)] for many triples in one GPU call."""
+    pk = np.stack([p.raw for p in pks])
+    sg = np.stack([s.raw for s in sigs])
+    return [bool(b) for b in engine().verify_batch(pk, sg, [bytes(m) for m in msgs])]
+
+
+def sign_batch(sks, msgs):
+    return [Signature(s) for s in engine().sign_batch(_frs([k.fr for k in sks]), [bytes(m) for m in msgs])]
+
+
+def combine_signatures_batch(pk_set, batches):
+    """PublicKeySet::combine_signatures for many messages signed under one key set.
+    Raises the first per-item error like the reference would for that item."""
+    t = pk_set.threshold()
+    items = [_samples(t, b) for b in batches]
+    xs = _frs([into_fr_plus_1(i) for it in items for i, _ in it])
+    pts = np.stack([s.raw for it in items for _, s in it])
+    out, st = engine().combine_g2_batch(len(items), t, xs, pts)
+    for s in st:
+        _raise(int(s))
+    return [Signature(o) for o in out]

@@ -18,11 +18,11 @@
 
 #if defined(__CUDACC__)
 #define TCB_HD __host__ __device__ __forceinline__
-#define TCB_HDN __host__ __device__ __noinline__
+#define TCB_HDN static __host__ __device__ __noinline__
 #define TCB_D __device__ __forceinline__
 #else
 #define TCB_HD inline __attribute__((always_inline))
-#define TCB_HDN __attribute__((noinline))
+#define TCB_HDN static __attribute__((noinline))
 #define TCB_D inline
 #endif
 

@@ -1,0 +1,118 @@
+// k_g1.cu — G1 kernels (one item per thread), Lagrange coefficients, Commitment::evaluate, roofline probes.
+#include "kern.h"
+#include "scheme.cuh"
+using namespace tcb;
+
+__global__ void __launch_bounds__(128) k_lagrange(size_t n, size_t m, const u8 *xs, u32 *lam, u8 *status) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    size_t item = t / m, i = t % m;
+    u8 st = 0;
+    lagrange_coeff(xs + item * m * 32, m, i, lam + 8 * t, st);
+    if (st) status[item] = st;
+}
+__global__ void __launch_bounds__(128) k_g1_mul(size_t n, const u8 *sk, const u8 *pts, u8 *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_g1_mul(i, sk, pts, out);
+}
+__global__ void __launch_bounds__(128) k_g1_mul_store(size_t units, const u32 *k, const u8 *pts, Jac1Store *out, u8 *status, size_t per_item) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < units) task_g1_mul_store(i, k, pts, out, status, per_item);
+}
+__global__ void __launch_bounds__(128) k_g1_sum(size_t n, size_t m, const Jac1Store *terms, u8 *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_g1(out + 96 * i, g1_sum(i, m, terms));
+}
+// PublicKeySet::decrypt tail: g = sum of terms (or the first share when t == 0), then xor_with_hash
+__global__ void __launch_bounds__(128) k_decrypt_finish(size_t n, size_t m, const Jac1Store *terms, const u8 *first_shares,
+                                                        const u8 *v, const u64 *voff, u8 *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Aff<Fp> g;
+    if (terms) g = g1_sum(i, m, terms);
+    else { bool ok = true; g = load_g1(first_shares + 96 * i, ok); }
+    xor_with_hash(out + voff[i], g, v + voff[i], (size_t)(voff[i + 1] - voff[i]));
+}
+__global__ void __launch_bounds__(128) k_g1_decode(size_t n, const u8 *pts, Jac1Store *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_g1_decode(i, pts, out);
+}
+__global__ void __launch_bounds__(128) k_commit_eval(size_t n, size_t deg, const Jac1Store *coeff, const u8 *x, u8 *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_commit_eval(i, deg, coeff, x, out);
+}
+
+static __device__ __forceinline__ u64 splitmix(u64 &s) {
+    u64 z = (s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+static __device__ Fp rand_fp(u64 &s, int mode) {
+    Fp r;
+    for (;;) {
+        for (int i = 0; i < 12; i += 2) { u64 v = splitmix(s); r.l[i] = (u32)v; r.l[i + 1] = (u32)(v >> 32); }
+        if (mode == 1) { for (int i = 0; i < 12; i++) r.l[i] = FpParams::mod(i); r.l[0] -= 1; return r; }
+        if (mode == 2) { for (int i = 0; i < 12; i++) r.l[i] = 0; return r; }
+        if (mode == 3) { for (int i = 0; i < 12; i++) r.l[i] = 0; r.l[0] = 1; return r; }
+        r.l[11] &= 0x1fffffffu;
+        if (limbs_lt_mod<FpParams>(r.l)) return r;
+    }
+}
+// 8 independent IMAD.WIDE accumulators per thread, no carries: the integer-MAC ceiling
+__global__ void __launch_bounds__(256) k_probe_imad(u64 *out, int iters, u32 seed) {
+    u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    u64 acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = k;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = (u64)a * (u32)(b + k) + acc[k];
+            a += (u32)acc[0];
+        }
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// 2 independent Montgomery-multiply chains per thread
+__global__ void __launch_bounds__(256) k_probe_fpmul(Fp *out, int iters, u64 seed) {
+    u64 s = seed + threadIdx.x + (u64)blockIdx.x * 1024;
+    Fp a = rand_fp(s, 0), b = rand_fp(s, 0), c = rand_fp(s, 0);
+    for (int it = 0; it < iters; it++) { a = a * c; b = b * c; }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a + b;
+}
+
+
+namespace tcbk {
+static inline unsigned grid1(size_t n) { return (unsigned)((n + 127) / 128); }
+cudaError_t upload_consts_g1(const Consts &c) { return cudaMemcpyToSymbol(d_consts, &c, sizeof c); }
+size_t g1_term_bytes() { return sizeof(Jac1Store); }
+size_t fp_bytes() { return sizeof(Fp); }
+void run_lagrange(cudaStream_t st, size_t n, size_t m, const u8 *xs, u32 *lam, u8 *status) {
+    if (n * m) k_lagrange<<<grid1(n * m), 128, 0, st>>>(n, m, xs, lam, status);
+}
+void run_g1_mul(cudaStream_t st, size_t n, const u8 *sk, const u8 *pts, u8 *out) {
+    if (n) k_g1_mul<<<grid1(n), 128, 0, st>>>(n, sk, pts, out);
+}
+void run_g1_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item) {
+    if (units) k_g1_mul_store<<<grid1(units), 128, 0, st>>>(units, k, pts, (Jac1Store *)terms, status, per_item);
+}
+void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out) {
+    if (n) k_g1_sum<<<grid1(n), 128, 0, st>>>(n, m, (const Jac1Store *)terms, out);
+}
+void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out) {
+    if (n) k_decrypt_finish<<<grid1(n), 128, 0, st>>>(n, m, (const Jac1Store *)terms, first_shares, v, voff, out);
+}
+void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab) {
+    if (n) k_g1_decode<<<grid1(n), 128, 0, st>>>(n, pts, (Jac1Store *)tab);
+}
+void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out) {
+    if (n) k_commit_eval<<<grid1(n), 128, 0, st>>>(n, deg, (const Jac1Store *)tab, x, out);
+}
+void run_probe_imad(cudaStream_t st, int blocks, int threads, u64 *out, int iters) { k_probe_imad<<<blocks, threads, 0, st>>>(out, iters, 12345u); }
+void run_probe_fpmul(cudaStream_t st, int blocks, int threads, void *out, int iters) { k_probe_fpmul<<<blocks, threads, 0, st>>>((Fp *)out, iters, 99ULL); }
+}  // namespace tcbk

@@ -1,0 +1,40 @@
+// k_g2.cu — G2 kernels on the lane-pair engine (Fp2S): hash_g2, sign, per-share terms and sums.
+#include "kern.h"
+#include "scheme.cuh"
+using namespace tcb;
+typedef Fp2S F2;
+
+static __device__ __forceinline__ size_t unit_index() { return ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1; }
+__global__ void __launch_bounds__(128) k_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out) {
+    size_t i = unit_index();
+    if (i < n) task_hash_g2<F2>(i, msgs, off, out);
+}
+__global__ void __launch_bounds__(128) k_sign(size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
+    size_t i = unit_index();
+    if (i < n) task_sign<F2>(i, sk, msgs, off, h, out);
+}
+__global__ void __launch_bounds__(128) k_g2_mul_store(size_t units, const u32 *k, const u8 *pts, JacStore<F2> *out, u8 *status, size_t per_item) {
+    size_t i = unit_index();
+    if (i < units) task_g2_mul_store<F2>(i, k, pts, out, status, per_item);
+}
+__global__ void __launch_bounds__(128) k_g2_sum(size_t n, size_t m, const JacStore<F2> *terms, u8 *out) {
+    size_t i = unit_index();
+    if (i < n) task_g2_sum<F2>(i, m, terms, out);
+}
+namespace tcbk {
+static inline unsigned grid2(size_t units) { return (unsigned)((units * 2 + 127) / 128); }
+cudaError_t upload_consts_g2(const Consts &c) { return cudaMemcpyToSymbol(d_consts, &c, sizeof c); }
+void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
+    if (n) k_hash_g2<<<grid2(n), 128, 0, st>>>(n, msgs, off, out);
+}
+void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
+    if (n) k_sign<<<grid2(n), 128, 0, st>>>(n, sk, msgs, off, h, out);
+}
+size_t g2_term_bytes() { return sizeof(JacStore<F2>); }
+void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item) {
+    if (units) k_g2_mul_store<<<grid2(units), 128, 0, st>>>(units, k, pts, (JacStore<F2> *)terms, status, per_item);
+}
+void run_g2_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out) {
+    if (n) k_g2_sum<<<grid2(n), 128, 0, st>>>(n, m, (const JacStore<F2> *)terms, out);
+}
+}  // namespace tcbk

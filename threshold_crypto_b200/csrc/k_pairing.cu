@@ -1,0 +1,166 @@
+// k_pairing.cu — the pairing-equality kernel (quad engine, quad.cuh) and the on-device self-tests.
+#include "kern.h"
+#include "quad.cuh"
+using namespace tcb;
+
+// one item per QUAD of lanes (quad.cuh); h_g2 replaces b_g2 when the hash was computed on device
+__global__ void __launch_bounds__(128, 2) k_verify_g2_quad(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (i >= n) return;
+    bool enc_ok;
+    bool res = pairing_eq_quad(a + 96 * i, b + 192 * i, c ? c + 96 * i : nullptr, d + 192 * i, enc_ok);
+    if ((threadIdx.x & 3) == 0) ok[i] = (res && enc_ok) ? 1 : 0;
+}
+// ---- self-test and roofline probes
+static __device__ __forceinline__ u64 splitmix(u64 &s) {
+    u64 z = (s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+static __device__ Fp rand_fp(u64 &s, int mode) {
+    Fp r;
+    for (;;) {
+        for (int i = 0; i < 12; i += 2) { u64 v = splitmix(s); r.l[i] = (u32)v; r.l[i + 1] = (u32)(v >> 32); }
+        if (mode == 1) { for (int i = 0; i < 12; i++) r.l[i] = FpParams::mod(i); r.l[0] -= 1; return r; }
+        if (mode == 2) { for (int i = 0; i < 12; i++) r.l[i] = 0; return r; }
+        if (mode == 3) { for (int i = 0; i < 12; i++) r.l[i] = 0; r.l[0] = 1; return r; }
+        r.l[11] &= 0x1fffffffu;
+        if (limbs_lt_mod<FpParams>(r.l)) return r;
+    }
+}
+__global__ void k_selftest_fp(size_t n, u64 seed, unsigned long long *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s = seed + i * 0x632be59bd9b4e019ULL;
+    int mode_a = i < 64 ? (int)(i & 3) : 0, mode_b = i < 64 ? (int)((i >> 2) & 3) : 0;
+    Fp a = rand_fp(s, mode_a), b = rand_fp(s, mode_b), c = rand_fp(s, 0), d = rand_fp(s, mode_a);
+    int errs = 0;
+    Fp ref = mont_mul_portable<FpParams>(a, b);
+    if ((a * b) != ref) errs++;
+    if (sqr(a) != mont_mul_portable<FpParams>(a, a)) errs++;
+    Fp d2 = dot2(a, b, c, d);
+    if (d2 != (ref + mont_mul_portable<FpParams>(c, d))) errs++;
+    if (((a + b) - b) != a) errs++;
+    if (!(a + (-a)).is_zero()) errs++;
+    if (!limbs_lt_mod<FpParams>((a + b).l) || !limbs_lt_mod<FpParams>((a - b).l) || !limbs_lt_mod<FpParams>(d2.l)) errs++;
+    // sliced Fp2 against scalar Fp2: lanes of a pair share (a,b,c,d) of the even lane
+    {
+        u32 m = 3u << (threadIdx.x & 30u);
+        Fp2 x, y;
+        x.c0 = a; x.c1 = b; y.c0 = c; y.c1 = d;
+        for (int k = 0; k < 12; k++) {
+            x.c0.l[k] = __shfl_sync(m, x.c0.l[k], threadIdx.x & 30u); x.c1.l[k] = __shfl_sync(m, x.c1.l[k], threadIdx.x & 30u);
+            y.c0.l[k] = __shfl_sync(m, y.c0.l[k], threadIdx.x & 30u); y.c1.l[k] = __shfl_sync(m, y.c1.l[k], threadIdx.x & 30u);
+        }
+        Fp2S xs = Fp2S::from_halves(x.c0, x.c1), ys = Fp2S::from_halves(y.c0, y.c1);
+        Fp2 pm = x * y, ps = sqr(x), px = mul_xi(x);
+        Fp2S qm = xs * ys, qs = sqr(xs), qx = mul_xi(xs);
+        bool role = threadIdx.x & 1;
+        if (qm.h != (role ? pm.c1 : pm.c0)) errs++;
+        if (qs.h != (role ? ps.c1 : ps.c0)) errs++;
+        if (qx.h != (role ? px.c1 : px.c0)) errs++;
+        // Fp2 mul against the schoolbook with portable multiplies
+        Fp t0 = mont_mul_portable<FpParams>(x.c0, y.c0) - mont_mul_portable<FpParams>(x.c1, y.c1);
+        Fp t1 = mont_mul_portable<FpParams>(x.c0, y.c1) + mont_mul_portable<FpParams>(x.c1, y.c0);
+        if (pm.c0 != t0 || pm.c1 != t1) errs++;
+        // predicates and rarely-used ops of the sliced engine against the scalar one
+        Fp2 z0 = x; z0.c1 = Fp::zero();          // only one half zero: exercises pair_and
+        Fp2S z0s = Fp2S::from_halves(z0.c0, z0.c1);
+        if (is_zero(z0s) != is_zero(z0)) errs++;
+        if (is_zero(Fp2S::zero()) != true) errs++;
+        if (eq(xs, ys) != eq(x, y) || !eq(xs, xs)) errs++;
+        if (eq(z0s, xs) != eq(z0, x)) errs++;
+        Fp2 pc = conj(x), pi = inv(x), pn = -x, pf = mul_fp(x, c);
+        Fp2S qc = conj(xs), qi = inv(xs), qn = -xs, qf = mul_fp(xs, c);
+        if (qc.h != (role ? pc.c1 : pc.c0)) errs++;
+        if (qi.h != (role ? pi.c1 : pi.c0)) errs++;
+        if (qn.h != (role ? pn.c1 : pn.c0)) errs++;
+        if (qf.h != (role ? pf.c1 : pf.c0)) errs++;
+        if (fp2_cmp(xs, ys) != fp2_cmp(x, y)) errs++;
+        if (norm(xs) != norm(x)) errs++;
+        Fp2 one_s; Fp2S::one().gather(one_s.c0, one_s.c1);
+        if (!eq(one_s, Fp2::one())) errs++;
+        if (((i >> 1) & 31) == 0) {   // a few square roots (expensive); the condition is pair-uniform
+            Fp2 sq = sqr(x), r1;
+            Fp2S r2;
+            bool ok1 = fp2_sqrt(r1, sq), ok2 = fp2_sqrt(r2, Fp2S::from_halves(sq.c0, sq.c1));
+            if (!ok1 || !ok2) errs++;
+            if (r2.h != (role ? r1.c1 : r1.c0)) errs++;
+            Fp2 nr;
+            bool ok3 = fp2_sqrt(nr, x), ok4 = fp2_sqrt(r2, xs);
+            if (ok3 != ok4) errs++;
+        }
+    }
+    if (errs) atomicAdd(bad, (unsigned long long)errs);
+}
+// quad-engine Fp12 ops (quad.cuh) against the scalar tower on random operands
+__device__ Fp12T<Fp2> rand_fp12(u64 &s) {
+    Fp12T<Fp2> r;
+    Fp *c = (Fp *)&r;
+    for (int k = 0; k < 12; k++) c[k] = rand_fp(s, 0);
+    return r;
+}
+__device__ Fp12Q to_quad(const Fp12T<Fp2> &a) {
+    const Fp6T<Fp2> &h = quad_pair() ? a.c1 : a.c0;
+    Fp12Q r;
+    r.h.c0 = Fp2S::from_halves(h.c0.c0, h.c0.c1);
+    r.h.c1 = Fp2S::from_halves(h.c1.c0, h.c1.c1);
+    r.h.c2 = Fp2S::from_halves(h.c2.c0, h.c2.c1);
+    return r;
+}
+__device__ int cmp_quad(const Fp12Q &q, const Fp12T<Fp2> &a) {
+    const Fp6T<Fp2> &h = quad_pair() ? a.c1 : a.c0;
+    bool role = threadIdx.x & 1;
+    int e = 0;
+    if (q.h.c0.h != (role ? h.c0.c1 : h.c0.c0)) e++;
+    if (q.h.c1.h != (role ? h.c1.c1 : h.c1.c0)) e++;
+    if (q.h.c2.h != (role ? h.c2.c1 : h.c2.c0)) e++;
+    return e;
+}
+__global__ void k_selftest_quad(size_t n, u64 seed, unsigned long long *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s = seed + (i >> 2) * 0x9e3779b97f4a7c15ULL;      // same stream on the 4 lanes of a quad
+    Fp12T<Fp2> a = rand_fp12(s), b = rand_fp12(s);
+    Fp2 l0, l1, l4;
+    l0.c0 = rand_fp(s, 0); l0.c1 = rand_fp(s, 0); l1.c0 = rand_fp(s, 0); l1.c1 = rand_fp(s, 0); l4.c0 = rand_fp(s, 0); l4.c1 = rand_fp(s, 0);
+    Fp12Q qa = to_quad(a), qb = to_quad(b);
+    int errs = 0;
+    errs += cmp_quad(fp12_sqr(qa), fp12_sqr(a));
+    errs += cmp_quad(fp12_mul(qa, qb), fp12_mul(a, b));
+    errs += cmp_quad(fp12_conj(qa), fp12_conj(a));
+    errs += cmp_quad(fp12_cyclo_sqr(qa), fp12_cyclo_sqr(a));
+    for (int k = 1; k <= 3; k++) errs += cmp_quad(fp12_frob(qa, k), fp12_frob(a, k));
+    {
+        Fp12T<Fp2> t = a; Fp12Q qt = qa;
+        fp12_mul_by_014(t, l0, l1, l4);
+        fp12_mul_by_014(qt, Fp2S::from_halves(l0.c0, l0.c1), Fp2S::from_halves(l1.c0, l1.c1), Fp2S::from_halves(l4.c0, l4.c1));
+        errs += cmp_quad(qt, t);
+    }
+    if (((i >> 2) & 15) == 0) {
+        errs += cmp_quad(fp12_inv(qa), fp12_inv(a));
+        if (fp12_is_one(fp12_mul(qa, fp12_inv(qa))) != true) errs++;
+        if (fp12_is_one(qa) != false) errs++;
+        if (fp12_is_one(q12_one()) != true) errs++;
+    }
+    if (((i >> 2) & 255) == 0) errs += cmp_quad(final_exponentiation(qa), final_exponentiation(a));
+    if (errs) atomicAdd(bad, (unsigned long long)errs);
+}
+
+namespace tcbk {
+cudaError_t upload_consts_pairing(const Consts &c) {
+    // the pairing kernel keeps its small call frames in L1: no shared-memory carve-out
+    cudaFuncSetAttribute(k_verify_g2_quad, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    return cudaMemcpyToSymbol(d_consts, &c, sizeof c);
+}
+void run_verify_g2_quad(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
+    if (!n) return;
+    size_t threads = n * 4;
+    k_verify_g2_quad<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, a, b, c, d, ok);
+}
+void run_selftest(cudaStream_t st, size_t n, u64 seed, unsigned long long *bad) {
+    k_selftest_fp<<<(unsigned)(n / 128), 128, 0, st>>>(n, seed, bad);
+    k_selftest_quad<<<(unsigned)(n / 128 / 8 + 1), 128, 0, st>>>(n / 8, seed ^ 0x5555, bad);
+}
+}  // namespace tcbk

@@ -1,0 +1,40 @@
+// kern.h — host-callable launchers of the kernels, one group per translation unit so the
+// groups compile in parallel (k_pairing.cu, k_g2.cu, k_g1.cu).  tcb200.cu (the C ABI) only
+// sees these prototypes.  Every launcher enqueues on `st` and returns; errors are picked up
+// by the caller with cudaGetLastError().
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "tower.cuh"
+
+namespace tcbk {
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// ---- k_pairing.cu
+cudaError_t upload_consts_pairing(const tcb::Consts &c);
+void run_verify_g2_quad(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok);
+void run_selftest(cudaStream_t st, size_t n, u64 seed, unsigned long long *bad);
+// ---- k_g2.cu  (lane-pair engine)
+cudaError_t upload_consts_g2(const tcb::Consts &c);
+void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out);
+void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out);
+size_t g2_term_bytes();
+void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item);
+void run_g2_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out);
+// ---- k_g1.cu
+cudaError_t upload_consts_g1(const tcb::Consts &c);
+size_t g1_term_bytes();
+void run_lagrange(cudaStream_t st, size_t n, size_t m, const u8 *xs, u32 *lam, u8 *status);
+void run_g1_mul(cudaStream_t st, size_t n, const u8 *sk, const u8 *pts, u8 *out);
+void run_g1_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item);
+void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out);
+void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
+void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
+void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);
+void run_probe_imad(cudaStream_t st, int blocks, int threads, u64 *out, int iters);
+void run_probe_fpmul(cudaStream_t st, int blocks, int threads, void *out, int iters);
+size_t fp_bytes();
+}  // namespace tcbk

@@ -1,0 +1,252 @@
+// quad.cuh — register-resident pairing-equality engine: FOUR lanes per item (device only).
+//
+// Why: with one item per thread (or per lane pair) an Fp12 accumulator is 144 (72) words per
+// thread, the Miller-loop state spills to local memory and the kernel becomes bound by L1/L2
+// latency at 2 warps/SMSP (profiles/r1_verify_pair.md).  Here an Fp12 value f = c0 + c1 w is
+// spread over a quad of lanes:
+//      lane = 2*j + e   (j = "pair", e = "role")   holds the Fp2-half e of every Fp2
+//      coefficient of c_j  ->  3 Fp = 36 registers per Fp12 value per lane.
+// Pair j additionally owns the G2 running point / line computation of pairing j of the
+// two-pairing product e(A,B) * e(-C,D), so both Miller loops advance in the same instruction
+// stream.  All exchanges are warp shuffles (xor 1 inside a pair, xor 2 across pairs); nothing
+// but the inputs and the final boolean touches memory.
+//
+// Fp6 arithmetic inside a pair is the generic Fp6T<Fp2S> code of tower.cuh.
+#pragma once
+#include "scheme.cuh"
+
+#if defined(__CUDACC__)
+namespace tcb {
+
+typedef Fp6T<Fp2S> Fp6S;
+
+TCB_D u32 quad_pair() { return (threadIdx.x >> 1) & 1u; }
+TCB_D u32 quad_mask() { return 0xFu << (threadIdx.x & 28u); }
+TCB_D Fp xq(const Fp &a) {   // exchange with the same role in the other pair of the quad
+    Fp r;
+    u32 m = quad_mask();
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = __shfl_xor_sync(m, a.l[i], 2);
+    return r;
+}
+TCB_D Fp2S xq(const Fp2S &a) { Fp2S r; r.h = xq(a.h); return r; }
+TCB_D Fp6S xq(const Fp6S &a) { Fp6S r; r.c0 = xq(a.c0); r.c1 = xq(a.c1); r.c2 = xq(a.c2); return r; }
+TCB_D bool quad_and(bool v) {
+    u32 m = quad_mask();
+    int a = __shfl_xor_sync(m, (int)v, 1);
+    bool t = v & (a != 0);
+    int b = __shfl_xor_sync(m, (int)t, 2);
+    return t & (b != 0);
+}
+TCB_D bool xq_flag(bool v) { return __shfl_xor_sync(quad_mask(), (int)v, 2) != 0; }
+TCB_D Fp6S sel6(bool c, const Fp6S &a, const Fp6S &b) {
+    Fp6S r; r.c0 = select(c, a.c0, b.c0); r.c1 = select(c, a.c1, b.c1); r.c2 = select(c, a.c2, b.c2); return r;
+}
+
+struct Fp12Q { Fp6S h; };   // pair 0: c0, pair 1: c1
+
+TCB_D Fp12Q q12_one() {
+    Fp12Q r;
+    r.h.c0 = quad_pair() ? Fp2S::zero() : Fp2S::one();
+    r.h.c1 = Fp2S::zero(); r.h.c2 = Fp2S::zero();
+    return r;
+}
+// complex squaring: pair 0 computes (a0+a1)(a0+v a1), pair 1 computes a0 a1
+__device__ __noinline__ Fp12Q fp12_sqr(const Fp12Q &a) {
+    bool p0 = quad_pair() == 0;
+    Fp6S o = xq(a.h);
+    Fp6S a0 = sel6(p0, a.h, o), a1 = sel6(p0, o, a.h);
+    Fp6S lhs = sel6(p0, a0 + a1, a0);
+    Fp6S rhs = sel6(p0, a0 + mul_v(a1), a1);
+    Fp6S x = fp6_mul(lhs, rhs);
+    Fp6S y = xq(x);                     // pair 0 receives ab
+    Fp12Q r;
+    r.h = sel6(p0, x - y - mul_v(y), x + x);
+    return r;
+}
+// pair 0: a0 b0 + v a1 b1;  pair 1: a0 b1 + a1 b0
+__device__ __noinline__ Fp12Q fp12_mul(const Fp12Q &a, const Fp12Q &b) {
+    bool p0 = quad_pair() == 0;
+    Fp6S oa = xq(a.h), ob = xq(b.h);
+    Fp6S m1 = fp6_mul(sel6(p0, a.h, oa), b.h);
+    Fp6S m2 = fp6_mul(sel6(p0, oa, a.h), ob);
+    Fp12Q r;
+    r.h = m1 + sel6(p0, mul_v(m2), m2);
+    return r;
+}
+// f * (l0 + l1 v + l4 v w); the line coefficients are pair-sliced Fp2S values present on BOTH pairs
+__device__ __noinline__ void fp12_mul_by_014(Fp12Q &f, const Fp2S &l0, const Fp2S &l1, const Fp2S &l4) {
+    bool p0 = quad_pair() == 0;
+    Fp6S o = xq(f.h);
+    Fp6S a = fp6_mul_by_01(f.h, l0, l1);
+    Fp6S b = fp6_mul_by_1(o, l4);
+    f.h = a + sel6(p0, mul_v(b), b);
+}
+TCB_D Fp12Q fp12_conj(const Fp12Q &a) {
+    Fp12Q r;
+    if (quad_pair()) r.h = -a.h; else r.h = a.h;
+    return r;
+}
+__device__ __noinline__ Fp12Q fp12_frob(const Fp12Q &a, int k) {
+    const Consts &C = CONSTS();
+    u32 j = quad_pair();
+    bool odd = k & 1;
+    Fp12Q r;
+    Fp2S t0 = odd ? conj(a.h.c0) : a.h.c0, t1 = odd ? conj(a.h.c1) : a.h.c1, t2 = odd ? conj(a.h.c2) : a.h.c2;
+    // coefficient v^i w^j has w-degree m = 2 i + j
+    r.h.c0 = j ? t0 * Fp2S::load(C.frob[k][1]) : t0;
+    r.h.c1 = t1 * Fp2S::load(C.frob[k][2 + j]);
+    r.h.c2 = t2 * Fp2S::load(C.frob[k][4 + j]);
+    return r;
+}
+__device__ __noinline__ Fp12Q fp12_inv(const Fp12Q &a) {
+    bool p0 = quad_pair() == 0;
+    Fp6S s = fp6_sqr(a.h);
+    Fp6S o = xq(s);
+    Fp6S t = sel6(p0, s - mul_v(o), o - mul_v(s));    // c0^2 - v c1^2 on both pairs
+    Fp6S ti = fp6_inv(t);
+    Fp12Q r;
+    Fp6S m = fp6_mul(a.h, ti);
+    if (p0) r.h = m; else r.h = -m;
+    return r;
+}
+TCB_D bool fp12_is_one(const Fp12Q &a) {
+    bool p0 = quad_pair() == 0;
+    Fp2S want = p0 ? Fp2S::one() : Fp2S::zero();
+    bool z = eq(a.h.c0, want);
+    z = is_zero(a.h.c1) & z;
+    z = is_zero(a.h.c2) & z;
+    return quad_and(z);
+}
+// Granger-Scott cyclotomic squaring.  With z0=c0.c0 z4=c0.c1 z3=c0.c2 (pair 0) and
+// z2=c1.c0 z1=c1.c1 z5=c1.c2 (pair 1):
+//   z0' = 3(z0^2 + xi z1^2) - 2 z0      z1' = 3(2 z0 z1) + 2 z1
+//   z4' = 3(z2^2 + xi z3^2) - 2 z4      z5' = 3(2 z2 z3) + 2 z5
+//   z3' = 3(z4^2 + xi z5^2) - 2 z3      z2' = 3 xi (2 z4 z5) + 2 z2
+// Each pair squares its own three coefficients; the three cross terms are (a+b)^2 - a^2 - b^2,
+// two of them computed on pair 0 and one on pair 1 (5 squaring slots per lane).
+__device__ __noinline__ Fp12Q fp12_cyclo_sqr(const Fp12Q &f) {
+    bool p0 = quad_pair() == 0;
+    Fp6S o = xq(f.h);                       // the other pair's coefficients
+    // own squares: pair 0: q0,q4,q3 ; pair 1: q2,q1,q5  (named by z index)
+    Fp6S q; q.c0 = sqr(f.h.c0); q.c1 = sqr(f.h.c1); q.c2 = sqr(f.h.c2);
+    Fp6S oq = xq(q);
+    // cross squares: slot A: pair 0 -> (z0+z1)^2 = (own.c0 + o.c1)^2 ; pair 1 -> (z2+z3)^2 = (own.c0 + o.c2)^2
+    Fp2S sa = sqr(f.h.c0 + select(p0, o.c1, o.c2));
+    // slot B: pair 0 -> (z4+z5)^2 = (own.c1 + o.c2)^2 ; pair 1 idles on the same operands (result unused)
+    Fp2S sb = sqr(f.h.c1 + o.c2);
+    // 2ab terms, all needed on pair 1:  2 z0 z1 = sa(p0) - q0 - q1 ; 2 z2 z3 = sa(p1) - q2 - q3 ; 2 z4 z5 = sb(p0) - q4 - q5
+    Fp2S sa_o = xq(sa), sb_o = xq(sb);
+    Fp12Q r;
+    if (p0) {
+        // own q = (q0, q4, q3), other oq = (q2, q1, q5)
+        Fp2S t0 = q.c0 + mul_xi(oq.c1);      // z0^2 + xi z1^2
+        Fp2S t1 = oq.c0 + mul_xi(q.c2);      // z2^2 + xi z3^2
+        Fp2S t2 = q.c1 + mul_xi(oq.c2);      // z4^2 + xi z5^2
+        Fp2S d;
+        d = t0 - f.h.c0; r.h.c0 = d + d + t0;        // z0'
+        d = t1 - f.h.c1; r.h.c1 = d + d + t1;        // z4'
+        d = t2 - f.h.c2; r.h.c2 = d + d + t2;        // z3'
+    } else {
+        // own q = (q2, q1, q5), other oq = (q0, q4, q3); own z = (z2, z1, z5)
+        Fp2S c01 = sa_o - oq.c0 - q.c1;      // 2 z0 z1
+        Fp2S c23 = sa - q.c0 - oq.c2;        // 2 z2 z3
+        Fp2S c45 = mul_xi(sb_o - oq.c1 - q.c2);   // xi * 2 z4 z5
+        Fp2S d;
+        d = c45 + f.h.c0; r.h.c0 = d + d + c45;      // z2'
+        d = c01 + f.h.c1; r.h.c1 = d + d + c01;      // z1'
+        d = c23 + f.h.c2; r.h.c2 = d + d + c23;      // z5'
+    }
+    return r;
+}
+__device__ __noinline__ Fp12Q fp12_exp_by_x(const Fp12Q &f, u64 x) {
+    Fp12Q acc = f;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    for (int i = top - 1; i >= 0; i--) {
+        acc = fp12_cyclo_sqr(acc);
+        if ((x >> i) & 1) acc = fp12_mul(acc, f);
+    }
+    return fp12_conj(acc);
+}
+// same chain as final_exponentiation<F2> in tower.cuh
+__device__ __noinline__ Fp12Q final_exponentiation(const Fp12Q &in) {
+    Fp12Q f2 = fp12_inv(in);
+    Fp12Q r = fp12_mul(fp12_conj(in), f2);
+    f2 = r;
+    r = fp12_mul(fp12_frob(r, 2), f2);
+    const u64 x = TCB_BLS_X;
+    Fp12Q y0 = fp12_cyclo_sqr(r);
+    Fp12Q y1 = fp12_exp_by_x(y0, x);
+    Fp12Q y2 = fp12_exp_by_x(y1, x >> 1);
+    Fp12Q y3 = fp12_conj(r);
+    y1 = fp12_mul(y1, y3);
+    y1 = fp12_conj(y1);
+    y1 = fp12_mul(y1, y2);
+    y2 = fp12_exp_by_x(y1, x);
+    y3 = fp12_exp_by_x(y2, x);
+    y1 = fp12_conj(y1);
+    y3 = fp12_mul(y3, y1);
+    y1 = fp12_conj(y1);
+    y1 = fp12_frob(y1, 3);
+    y2 = fp12_frob(y2, 2);
+    y1 = fp12_mul(y1, y2);
+    y2 = fp12_exp_by_x(y3, x);
+    y2 = fp12_mul(y2, y0);
+    y2 = fp12_mul(y2, r);
+    y1 = fp12_mul(y1, y2);
+    y2 = fp12_frob(y3, 1);
+    return fp12_mul(y1, y2);
+}
+
+// ----------------------------------------------------------------------------- two-pairing Miller loop on a quad
+// Pair j holds (P_j, Q_j) and the running point T_j.  Per step each pair evaluates its own
+// line, the lines are swapped across pairs (36 words) and f is multiplied by both.
+struct LineS { Fp2S c0, c1, c4; };   // l0 + l1 v + l4 v w, already scaled by P
+TCB_D LineS xq(const LineS &l) { LineS r; r.c0 = xq(l.c0); r.c1 = xq(l.c1); r.c4 = xq(l.c4); return r; }
+TCB_D LineS scale_line(const Line<Fp2S> &l, const Aff<Fp> &p) {
+    LineS r;
+    r.c0 = l.c; r.c1 = mul_fp(l.b, p.x); r.c4 = mul_fp(l.a, p.y);
+    return r;
+}
+TCB_D void apply_lines(Fp12Q &f, const LineS &mine, bool act_mine, bool act_other) {
+    bool p0 = quad_pair() == 0;
+    LineS other = xq(mine);
+    // line of pairing 0 first, then pairing 1 (same order on all four lanes)
+    bool act0 = p0 ? act_mine : act_other, act1 = p0 ? act_other : act_mine;
+    if (act0) fp12_mul_by_014(f, select(p0, mine.c0, other.c0), select(p0, mine.c1, other.c1), select(p0, mine.c4, other.c4));
+    if (act1) fp12_mul_by_014(f, select(p0, other.c0, mine.c0), select(p0, other.c1, mine.c1), select(p0, other.c4, mine.c4));
+}
+// e(a,b) == e(c,d), evaluated by one quad.  Every lane passes the pointers of the item; pair 0
+// loads (a, b), pair 1 loads (-c, d).
+__device__ __noinline__ bool pairing_eq_quad(const u8 *a_g1, const u8 *b_g2, const u8 *c_g1, const u8 *d_g2, bool &ok_enc) {
+    bool p0 = quad_pair() == 0;
+    bool ok = true;
+    Aff<Fp> p;
+    if (p0) p = load_g1(a_g1, ok);
+    else if (c_g1) { p = load_g1(c_g1, ok); p.y = -p.y; }
+    else { p.x = CONSTS().g1x; p.y = -CONSTS().g1y; p.inf = false; }
+    Aff<Fp2S> q = load_g2<Fp2S>(p0 ? b_g2 : d_g2, ok);
+    bool act = !(p.inf || q.inf);
+    bool act_o = xq_flag(act);
+    ok_enc = quad_and(ok);
+    Jac<Fp2S> t = jac_from_aff(q);
+    Fp12Q f = q12_one();
+    const u64 xs = TCB_BLS_X >> 1;
+    for (int i = 61; i >= 0; i--) {
+        LineS l = scale_line(doubling_step(t), p);
+        apply_lines(f, l, act, act_o);
+        if ((xs >> i) & 1) {
+            l = scale_line(addition_step(t, q), p);
+            apply_lines(f, l, act, act_o);
+        }
+        f = fp12_sqr(f);
+    }
+    LineS l = scale_line(doubling_step(t), p);
+    apply_lines(f, l, act, act_o);
+    f = fp12_conj(f);
+    return fp12_is_one(final_exponentiation(f));
+}
+
+}  // namespace tcb
+#endif

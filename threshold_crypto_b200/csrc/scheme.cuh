@@ -193,23 +193,121 @@ TCB_HD Fp fp_random(ChaChaRng &g) {
         if (limbs_lt_mod<FpParams>(r.l)) return r;
     }
 }
-// EXTERNAL pairing 0.16 G2::random (A2, A3) followed by the exact-cofactor multiplication.
+// ---- helpers that make the sampling loop work for both engines (1 or 2 lanes per item)
+template <class F2>
+TCB_HD int vote_first(bool ok_me) {   // lowest lane of the unit whose flag is set, or -1 (uniform over the unit)
+#if defined(__CUDA_ARCH__)
+    if (F2::SLICED) {
+        bool o = __shfl_xor_sync(pair_mask(), (int)ok_me, 1) != 0;
+        bool role = lane_role();
+        bool ok0 = role ? o : ok_me, ok1 = role ? ok_me : o;
+        return ok0 ? 0 : (ok1 ? 1 : -1);
+    }
+#endif
+    return ok_me ? 0 : -1;
+}
+template <class F2>
+TCB_HD Fp bcast_fp(const Fp &v, int src) {   // value held by lane `src` of the unit
+#if defined(__CUDA_ARCH__)
+    if (F2::SLICED) {
+        Fp r;
+        u32 m = pair_mask();
+        int lane = (int)((threadIdx.x & 30u) | (u32)src);
+#pragma unroll
+        for (int i = 0; i < 12; i++) r.l[i] = __shfl_sync(m, v.l[i], lane);
+        return r;
+    }
+#endif
+    return v;
+}
+template <class F2>
+TCB_HD bool bcast_flag(bool v, int src) {
+#if defined(__CUDA_ARCH__)
+    if (F2::SLICED) return __shfl_sync(pair_mask(), (int)v, (int)((threadIdx.x & 30u) | (u32)src)) != 0;
+#endif
+    return v;
+}
+// a / 2 mod p (valid on Montgomery representatives as well)
+TCB_HD Fp fp_half(const Fp &a) {
+    u32 mask = (a.l[0] & 1u) ? 0xffffffffu : 0u;
+    u32 t[12], hi;
+    add_cc(t[0], a.l[0], FpParams::mod(0) & mask);
+#pragma unroll
+    for (int i = 1; i < 12; i++) addc_cc(t[i], a.l[i], FpParams::mod(i) & mask);
+    addc(hi, 0, 0);
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 11; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    r.l[11] = (t[11] >> 1) | (hi << 31);
+    return r;
+}
+// EXTERNAL pairing 0.16 G2::random (A2, A3): x = Fq2::random, greatest = next_u32() % 2,
+// y = sqrt(x^3 + b) picked by (y < -y) ^ greatest, multiplied by the exact cofactor h2, retry on
+// no root / zero.  The candidates are consumed from the ChaCha stream in the reference's order;
+// HOW a candidate is tested and the root extracted is free (any root gives the same point after
+// the ordering rule):
+//   * residuosity + first half of the square root: s = sqrt(norm(a)) in Fp by one Fp power;
+//     an engine with two lanes per item tests two consecutive candidates per round;
+//   * y0 = sqrt((a0 +- s)/2), y1 = a1 / (2 y0) with e = delta^((p-3)/4): y0 = delta e, 1/y0 = e;
+//     the two lanes try the two signs at once;
+//   * the cofactor multiplication runs AFTER the rejection loop (all lanes converged) and uses
+//     the psi-endomorphism identity of g2_clear_cofactor.
 template <class F2>
 TCB_HDN Jac<F2> g2_random(ChaChaRng &g) {
     const Consts &C = CONSTS();
-    F2 b2 = F2::from_halves(C.b1, C.b1);   // 4 (1 + u)
+    constexpr int L = F2::SLICED ? 2 : 1;
+    const int me = (int)my_role<F2>();
+    Fp2 b2;
+    b2.c0 = C.b1; b2.c1 = C.b1;   // 4 (1 + u)
     for (;;) {
-        Fp c0 = fp_random(g);
-        Fp c1 = fp_random(g);
-        bool greatest = (rng_u32(g) & 1u) != 0;
-        F2 x = F2::from_halves(c0, c1);
+        Fp2 x, a;
+        Fp s;
+        bool greatest;
+        for (;;) {
+            Fp2 xc;
+            bool gr = false;
+            xc.c0 = Fp::zero(); xc.c1 = Fp::zero();
+            for (int k = 0; k < L; k++) {
+                Fp c0 = fp_random(g);
+                Fp c1 = fp_random(g);
+                bool gk = (rng_u32(g) & 1u) != 0;
+                if (k == me) { xc.c0 = c0; xc.c1 = c1; gr = gk; }
+            }
+            Fp2 ac = sqr(xc) * xc + b2;
+            Fp nrm = norm(ac);
+            Fp sc = fp_pow<ExpPp1d4>(nrm);
+            int w = vote_first<F2>(sqr(sc) == nrm);
+            if (w < 0) continue;
+            x.c0 = bcast_fp<F2>(xc.c0, w); x.c1 = bcast_fp<F2>(xc.c1, w);
+            a.c0 = bcast_fp<F2>(ac.c0, w); a.c1 = bcast_fp<F2>(ac.c1, w);
+            s = bcast_fp<F2>(sc, w);
+            greatest = bcast_flag<F2>(gr, w);
+            break;
+        }
         F2 y;
-        if (!fp2_sqrt(y, sqr(x) * x + b2)) continue;
+        if (a.c1.is_zero()) {
+            fp2_sqrt(y, F2::from_halves(a.c0, a.c1));   // a in Fp: generic Algorithm 9 (never hit by random x)
+        } else {
+            Fp y0 = Fp::zero(), y1 = Fp::zero();
+            for (int r = 0; r < 2 / L; r++) {   // exactly one of (a0 + s)/2, (a0 - s)/2 is a square
+                int which = r * L + me;
+                Fp d = fp_half(which == 0 ? a.c0 + s : a.c0 - s);
+                Fp e = fp_pow<ExpPm3d4>(d);
+                Fp c = d * e;
+                int w = vote_first<F2>(sqr(c) == d);
+                if (w >= 0) {
+                    y0 = bcast_fp<F2>(c, w);
+                    y1 = bcast_fp<F2>(fp_half(a.c1 * e), w);
+                    break;
+                }
+            }
+            y = F2::from_halves(y0, y1);
+        }
         F2 ny = -y;
         bool pick_y = (fp2_cmp(y, ny) < 0) != greatest;
-        Aff<F2> a;
-        a.x = x; a.y = select(pick_y, y, ny); a.inf = false;
-        Jac<F2> p = jac_mul_const<F2, ExpH2>(a);
+        Aff<F2> pt;
+        pt.x = F2::from_halves(x.c0, x.c1); pt.y = select(pick_y, y, ny); pt.inf = false;
+        Jac<F2> p = g2_clear_cofactor(pt);
         if (!jac_is_inf(p)) return p;
     }
 }
@@ -450,6 +548,10 @@ inline void build_consts(Consts &C) {
         for (int m = 0; m < 6; m++) { acc.store(C.frob[k][m]); acc = acc * g[k]; }
     }
     for (int m = 0; m < 6; m++) Fp2::one().store(C.frob[0][m]);
+    h_consts = C;
+    // psi(x, y) = (conj(x) / xi^((p-1)/3), conj(y) / xi^((p-1)/2))
+    inv(Fp2::load(C.frob[1][2])).store(C.psi_x);
+    inv(Fp2::load(C.frob[1][3])).store(C.psi_y);
     h_consts = C;
 }
 

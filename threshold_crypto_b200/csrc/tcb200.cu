@@ -1,209 +1,28 @@
-// tcb200.cu — sm_100a kernels and the extern "C" boundary (include/tcb200.h) of the
-// B200-native threshold_crypto hot path.  No CPU fallback: every entry point launches CUDA
-// kernels or fails with an error code.
+// tcb200.cu — the extern "C" boundary (include/tcb200.h) of the B200-native threshold_crypto
+// hot path: context, scratch arena, host<->device staging, device sharding, kernel sequencing.
+// The kernels live in k_pairing.cu / k_g2.cu / k_g1.cu (launchers in kern.h).  No CPU fallback:
+// every entry point enqueues CUDA kernels or fails with an error code.
 //
-// Kernel inventory (one unit = one thread, or one lane pair for the Fp2S engine):
-//   k_verify_g2 / k_verify      a1/a3  pairing equality (+ on-device hash_g2)
-//   k_hash_g2                   a2     SHA3 -> ChaCha20 -> G2::random -> x h2
-//   k_sign                      a4     sk * H(m)
+// Kernel inventory:
+//   k_verify_g2_quad            a1/a3  pairing equality, one item per lane QUAD (quad.cuh)
+//   k_hash_g2                   a2     SHA3 -> ChaCha20 -> G2::random -> exact cofactor (lane pairs)
+//   k_sign                      a4     sk * H(m)                                   (lane pairs)
 //   k_lagrange                  a5     lambda_i(0), one thread per (item, share)
 //   k_g2_mul_store / k_g2_sum   a6     per-share terms and their sum (combine_signatures)
 //   k_g1_mul / k_g1_mul_store / k_g1_sum / k_decrypt_finish   a7 (decrypt shares, decrypt)
 //   k_g1_decode / k_commit_eval a8     Commitment::evaluate (Horner)
-//   k_selftest_fp, k_probe_*    measurement / self-test
+//   k_selftest_*, k_probe_*     measurement / self-test
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
 #include <cstdio>
 #include <cstring>
 #include "../../include/tcb200.h"
+#include "kern.h"
 #include "scheme.cuh"
 
 using namespace tcb;
-
-// ----------------------------------------------------------------------------- kernels
-template <class F2> __device__ __forceinline__ size_t unit_index() {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    return F2::SLICED ? (t >> 1) : t;
-}
-template <class F2>
-__global__ void __launch_bounds__(128) k_verify_g2(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
-    size_t i = unit_index<F2>();
-    if (i < n) task_verify_g2<F2>(i, a, b, c, d, ok);
-}
-template <class F2>
-__global__ void __launch_bounds__(128) k_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out) {
-    size_t i = unit_index<F2>();
-    if (i < n) task_hash_g2<F2>(i, msgs, off, out);
-}
-template <class F2>
-__global__ void __launch_bounds__(128) k_verify(size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
-    size_t i = unit_index<F2>();
-    if (i < n) task_verify<F2>(i, pk, sig, msgs, off, ok);
-}
-template <class F2>
-__global__ void __launch_bounds__(128) k_sign(size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
-    size_t i = unit_index<F2>();
-    if (i < n) task_sign<F2>(i, sk, msgs, off, h, out);
-}
-__global__ void __launch_bounds__(128) k_lagrange(size_t n, size_t m, const u8 *xs, u32 *lam, u8 *status) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * m) return;
-    size_t item = t / m, i = t % m;
-    u8 st = 0;
-    lagrange_coeff(xs + item * m * 32, m, i, lam + 8 * t, st);
-    if (st) status[item] = st;
-}
-template <class F2>
-__global__ void __launch_bounds__(128) k_g2_mul_store(size_t units, const u32 *k, const u8 *pts, JacStore<F2> *out, u8 *status, size_t per_item) {
-    size_t i = unit_index<F2>();
-    if (i < units) task_g2_mul_store<F2>(i, k, pts, out, status, per_item);
-}
-template <class F2>
-__global__ void __launch_bounds__(128) k_g2_sum(size_t n, size_t m, const JacStore<F2> *terms, u8 *out) {
-    size_t i = unit_index<F2>();
-    if (i < n) task_g2_sum<F2>(i, m, terms, out);
-}
-__global__ void __launch_bounds__(128) k_g1_mul(size_t n, const u8 *sk, const u8 *pts, u8 *out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) task_g1_mul(i, sk, pts, out);
-}
-__global__ void __launch_bounds__(128) k_g1_mul_store(size_t units, const u32 *k, const u8 *pts, Jac1Store *out, u8 *status, size_t per_item) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < units) task_g1_mul_store(i, k, pts, out, status, per_item);
-}
-__global__ void __launch_bounds__(128) k_g1_sum(size_t n, size_t m, const Jac1Store *terms, u8 *out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) store_g1(out + 96 * i, g1_sum(i, m, terms));
-}
-// PublicKeySet::decrypt tail: g = sum of terms (or the first share when t == 0), then xor_with_hash
-__global__ void __launch_bounds__(128) k_decrypt_finish(size_t n, size_t m, const Jac1Store *terms, const u8 *first_shares,
-                                                        const u8 *v, const u64 *voff, u8 *out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Aff<Fp> g;
-    if (terms) g = g1_sum(i, m, terms);
-    else { bool ok = true; g = load_g1(first_shares + 96 * i, ok); }
-    xor_with_hash(out + voff[i], g, v + voff[i], (size_t)(voff[i + 1] - voff[i]));
-}
-__global__ void __launch_bounds__(128) k_g1_decode(size_t n, const u8 *pts, Jac1Store *out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) task_g1_decode(i, pts, out);
-}
-__global__ void __launch_bounds__(128) k_commit_eval(size_t n, size_t deg, const Jac1Store *coeff, const u8 *x, u8 *out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) task_commit_eval(i, deg, coeff, x, out);
-}
-
-// ---- self-test and roofline probes
-__device__ __forceinline__ u64 splitmix(u64 &s) {
-    u64 z = (s += 0x9e3779b97f4a7c15ULL);
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
-    return z ^ (z >> 31);
-}
-__device__ Fp rand_fp(u64 &s, int mode) {
-    Fp r;
-    for (;;) {
-        for (int i = 0; i < 12; i += 2) { u64 v = splitmix(s); r.l[i] = (u32)v; r.l[i + 1] = (u32)(v >> 32); }
-        if (mode == 1) { for (int i = 0; i < 12; i++) r.l[i] = FpParams::mod(i); r.l[0] -= 1; return r; }
-        if (mode == 2) { for (int i = 0; i < 12; i++) r.l[i] = 0; return r; }
-        if (mode == 3) { for (int i = 0; i < 12; i++) r.l[i] = 0; r.l[0] = 1; return r; }
-        r.l[11] &= 0x1fffffffu;
-        if (limbs_lt_mod<FpParams>(r.l)) return r;
-    }
-}
-__global__ void k_selftest_fp(size_t n, u64 seed, unsigned long long *bad) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u64 s = seed + i * 0x632be59bd9b4e019ULL;
-    int mode_a = i < 64 ? (int)(i & 3) : 0, mode_b = i < 64 ? (int)((i >> 2) & 3) : 0;
-    Fp a = rand_fp(s, mode_a), b = rand_fp(s, mode_b), c = rand_fp(s, 0), d = rand_fp(s, mode_a);
-    int errs = 0;
-    Fp ref = mont_mul_portable<FpParams>(a, b);
-    if ((a * b) != ref) errs++;
-    if (sqr(a) != mont_mul_portable<FpParams>(a, a)) errs++;
-    Fp d2 = dot2(a, b, c, d);
-    if (d2 != (ref + mont_mul_portable<FpParams>(c, d))) errs++;
-    if (((a + b) - b) != a) errs++;
-    if (!(a + (-a)).is_zero()) errs++;
-    if (!limbs_lt_mod<FpParams>((a + b).l) || !limbs_lt_mod<FpParams>((a - b).l) || !limbs_lt_mod<FpParams>(d2.l)) errs++;
-    // sliced Fp2 against scalar Fp2: lanes of a pair share (a,b,c,d) of the even lane
-    {
-        u32 m = 3u << (threadIdx.x & 30u);
-        Fp2 x, y;
-        x.c0 = a; x.c1 = b; y.c0 = c; y.c1 = d;
-        for (int k = 0; k < 12; k++) {
-            x.c0.l[k] = __shfl_sync(m, x.c0.l[k], threadIdx.x & 30u); x.c1.l[k] = __shfl_sync(m, x.c1.l[k], threadIdx.x & 30u);
-            y.c0.l[k] = __shfl_sync(m, y.c0.l[k], threadIdx.x & 30u); y.c1.l[k] = __shfl_sync(m, y.c1.l[k], threadIdx.x & 30u);
-        }
-        Fp2S xs = Fp2S::from_halves(x.c0, x.c1), ys = Fp2S::from_halves(y.c0, y.c1);
-        Fp2 pm = x * y, ps = sqr(x), px = mul_xi(x);
-        Fp2S qm = xs * ys, qs = sqr(xs), qx = mul_xi(xs);
-        bool role = threadIdx.x & 1;
-        if (qm.h != (role ? pm.c1 : pm.c0)) errs++;
-        if (qs.h != (role ? ps.c1 : ps.c0)) errs++;
-        if (qx.h != (role ? px.c1 : px.c0)) errs++;
-        // Fp2 mul against the schoolbook with portable multiplies
-        Fp t0 = mont_mul_portable<FpParams>(x.c0, y.c0) - mont_mul_portable<FpParams>(x.c1, y.c1);
-        Fp t1 = mont_mul_portable<FpParams>(x.c0, y.c1) + mont_mul_portable<FpParams>(x.c1, y.c0);
-        if (pm.c0 != t0 || pm.c1 != t1) errs++;
-        // predicates and rarely-used ops of the sliced engine against the scalar one
-        Fp2 z0 = x; z0.c1 = Fp::zero();          // only one half zero: exercises pair_and
-        Fp2S z0s = Fp2S::from_halves(z0.c0, z0.c1);
-        if (is_zero(z0s) != is_zero(z0)) errs++;
-        if (is_zero(Fp2S::zero()) != true) errs++;
-        if (eq(xs, ys) != eq(x, y) || !eq(xs, xs)) errs++;
-        if (eq(z0s, xs) != eq(z0, x)) errs++;
-        Fp2 pc = conj(x), pi = inv(x), pn = -x, pf = mul_fp(x, c);
-        Fp2S qc = conj(xs), qi = inv(xs), qn = -xs, qf = mul_fp(xs, c);
-        if (qc.h != (role ? pc.c1 : pc.c0)) errs++;
-        if (qi.h != (role ? pi.c1 : pi.c0)) errs++;
-        if (qn.h != (role ? pn.c1 : pn.c0)) errs++;
-        if (qf.h != (role ? pf.c1 : pf.c0)) errs++;
-        if (fp2_cmp(xs, ys) != fp2_cmp(x, y)) errs++;
-        if (norm(xs) != norm(x)) errs++;
-        Fp2 one_s; Fp2S::one().gather(one_s.c0, one_s.c1);
-        if (!eq(one_s, Fp2::one())) errs++;
-        if (((i >> 1) & 31) == 0) {   // a few square roots (expensive); the condition is pair-uniform
-            Fp2 sq = sqr(x), r1;
-            Fp2S r2;
-            bool ok1 = fp2_sqrt(r1, sq), ok2 = fp2_sqrt(r2, Fp2S::from_halves(sq.c0, sq.c1));
-            if (!ok1 || !ok2) errs++;
-            if (r2.h != (role ? r1.c1 : r1.c0)) errs++;
-            Fp2 nr;
-            bool ok3 = fp2_sqrt(nr, x), ok4 = fp2_sqrt(r2, xs);
-            if (ok3 != ok4) errs++;
-        }
-    }
-    if (errs) atomicAdd(bad, (unsigned long long)errs);
-}
-// 8 independent IMAD.WIDE accumulators per thread, no carries: the integer-MAC ceiling
-__global__ void __launch_bounds__(256) k_probe_imad(u64 *out, int iters, u32 seed) {
-    u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-    u64 acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = (u64)a * (u32)(b + k) + acc[k];
-            a += (u32)acc[0];
-        }
-    }
-    u64 s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-// 2 independent Montgomery-multiply chains per thread
-__global__ void __launch_bounds__(256) k_probe_fpmul(Fp *out, int iters, u64 seed) {
-    u64 s = seed + threadIdx.x + (u64)blockIdx.x * 1024;
-    Fp a = rand_fp(s, 0), b = rand_fp(s, 0), c = rand_fp(s, 0);
-    for (int it = 0; it < iters; it++) { a = a * c; b = b * c; }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a + b;
-}
+using namespace tcbk;
 
 // ----------------------------------------------------------------------------- context
 struct Chunk { void *p; size_t sz, used; };
@@ -217,7 +36,7 @@ struct tcb_ctx {
     std::vector<DevState> devs;
     std::string err;
     uint64_t launches = 0;
-    int engine = TCB_ENGINE_PAIR;
+    int engine = TCB_ENGINE_QUAD;
     int sm_count = 148;
 };
 
@@ -263,32 +82,35 @@ static void *arena_alloc(tcb_ctx *ctx, DevState &d, size_t bytes) {
     return p;
 }
 
-template <class K, class... A>
-static int launch(tcb_ctx *ctx, cudaStream_t st, K kern, size_t threads, A... args) {
-    if (threads == 0) return 0;
-    const int block = 128;
-    size_t grid = (threads + block - 1) / block;
-    kern<<<(unsigned)grid, block, 0, st>>>(args...);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-#define LAUNCH_G2(kern, units, ...)                                                                       \
-    (ctx->engine == TCB_ENGINE_PAIR ? launch(ctx, st, kern<Fp2S>, (size_t)(units) * 2, __VA_ARGS__)       \
-                                    : launch(ctx, st, kern<Fp2>, (size_t)(units), __VA_ARGS__))
+// count a launch and pick up launch errors
+#define RUN(call)                      \
+    do {                               \
+        call;                          \
+        ctx->launches++;               \
+        CK(cudaGetLastError());        \
+    } while (0)
 
 // ----------------------------------------------------------------------------- device-side implementations
 static int impl_verify_g2(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
-    return LAUNCH_G2(k_verify_g2, n, n, a, b, c, d, ok);
+    if (n) RUN(run_verify_g2_quad(st, n, a, b, c, d, ok));
+    return 0;
 }
 static int impl_hash_g2(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
-    return LAUNCH_G2(k_hash_g2, n, n, msgs, off, out);
+    if (n) RUN(run_hash_g2(st, n, msgs, off, out));
+    return 0;
 }
-static int impl_verify(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
-    return LAUNCH_G2(k_verify, n, n, pk, sig, msgs, off, ok);
+static int impl_verify(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
+    if (!n) return 0;
+    // hash_g2 on lane pairs into scratch, then the quad pairing check e(pk, H) == e(g1, sig)
+    u8 *h = (u8 *)arena_alloc(ctx, d, n * 192);
+    if (!h) return -1;
+    RUN(run_hash_g2(st, n, msgs, off, h));
+    RUN(run_verify_g2_quad(st, n, pk, h, nullptr, sig, ok));
+    return 0;
 }
 static int impl_sign(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
-    return LAUNCH_G2(k_sign, n, n, sk, msgs, off, h, out);
+    if (n) RUN(run_sign(st, n, sk, msgs, off, h, out));
+    return 0;
 }
 static int impl_combine_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     CK(cudaMemsetAsync(status, 0, n, st));
@@ -296,18 +118,12 @@ static int impl_combine_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n,
     if (t == 0) { CK(cudaMemcpyAsync(out, shares, n * 192, cudaMemcpyDeviceToDevice, st)); return 0; }
     size_t m = t + 1;
     u32 *lam = (u32 *)arena_alloc(ctx, d, n * m * 32);
-    if (!lam) return -1;
-    if (launch(ctx, st, k_lagrange, n * m, n, m, x, lam, status)) return -1;
-    if (ctx->engine == TCB_ENGINE_PAIR) {
-        JacStore<Fp2S> *terms = (JacStore<Fp2S> *)arena_alloc(ctx, d, n * m * sizeof(JacStore<Fp2S>));
-        if (!terms) return -1;
-        if (launch(ctx, st, k_g2_mul_store<Fp2S>, n * m * 2, n * m, lam, shares, terms, status, m)) return -1;
-        return launch(ctx, st, k_g2_sum<Fp2S>, n * 2, n, m, terms, out);
-    }
-    JacStore<Fp2> *terms = (JacStore<Fp2> *)arena_alloc(ctx, d, n * m * sizeof(JacStore<Fp2>));
-    if (!terms) return -1;
-    if (launch(ctx, st, k_g2_mul_store<Fp2>, n * m, n * m, lam, shares, terms, status, m)) return -1;
-    return launch(ctx, st, k_g2_sum<Fp2>, n, n, m, terms, out);
+    void *terms = arena_alloc(ctx, d, n * m * g2_term_bytes());
+    if (!lam || !terms) return -1;
+    RUN(run_lagrange(st, n, m, x, lam, status));
+    RUN(run_g2_mul_store(st, n * m, lam, shares, terms, status, m));
+    RUN(run_g2_sum(st, n, m, terms, out));
+    return 0;
 }
 // mode 0: write the combined G1 point; mode 1: xor_with_hash (decrypt)
 static int impl_combine_g1(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t t, const u8 *x, const u8 *shares,
@@ -316,22 +132,25 @@ static int impl_combine_g1(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n,
     if (n == 0) return 0;
     if (t == 0) {
         if (mode == 0) { CK(cudaMemcpyAsync(out, shares, n * 96, cudaMemcpyDeviceToDevice, st)); return 0; }
-        return launch(ctx, st, k_decrypt_finish, n, n, (size_t)1, (const Jac1Store *)nullptr, shares, v, voff, out);
+        RUN(run_decrypt_finish(st, n, 1, nullptr, shares, v, voff, out));
+        return 0;
     }
     size_t m = t + 1;
     u32 *lam = (u32 *)arena_alloc(ctx, d, n * m * 32);
-    Jac1Store *terms = (Jac1Store *)arena_alloc(ctx, d, n * m * sizeof(Jac1Store));
+    void *terms = arena_alloc(ctx, d, n * m * g1_term_bytes());
     if (!lam || !terms) return -1;
-    if (launch(ctx, st, k_lagrange, n * m, n, m, x, lam, status)) return -1;
-    if (launch(ctx, st, k_g1_mul_store, n * m, n * m, lam, shares, terms, status, m)) return -1;
-    if (mode == 0) return launch(ctx, st, k_g1_sum, n, n, m, terms, out);
-    return launch(ctx, st, k_decrypt_finish, n, n, m, (const Jac1Store *)terms, shares, v, voff, out);
+    RUN(run_lagrange(st, n, m, x, lam, status));
+    RUN(run_g1_mul_store(st, n * m, lam, shares, terms, status, m));
+    if (mode == 0) RUN(run_g1_sum(st, n, m, terms, out));
+    else RUN(run_decrypt_finish(st, n, m, terms, shares, v, voff, out));
+    return 0;
 }
 static int impl_commit_eval(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
-    Jac1Store *tab = (Jac1Store *)arena_alloc(ctx, d, (deg + 1) * sizeof(Jac1Store));
+    void *tab = arena_alloc(ctx, d, (deg + 1) * g1_term_bytes());
     if (!tab) return -1;
-    if (launch(ctx, st, k_g1_decode, deg + 1, deg + 1, coeff, tab)) return -1;
-    return launch(ctx, st, k_commit_eval, n, n, deg, (const Jac1Store *)tab, x, out);
+    RUN(run_g1_decode(st, deg + 1, coeff, tab));
+    if (n) RUN(run_commit_eval(st, n, deg, tab, x, out));
+    return 0;
 }
 
 // ----------------------------------------------------------------------------- init / free
@@ -357,7 +176,7 @@ extern "C" int tcb_init(tcb_ctx **out, const int *device_ids, int n_devices) {
         if (d.dev < 0 || d.dev >= count) { delete ctx; return -4; }
         if (cudaSetDevice(d.dev) != cudaSuccess) { delete ctx; return -5; }
         if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -6; }
-        if (cudaMemcpyToSymbol(d_consts, &C, sizeof C) != cudaSuccess) { delete ctx; return -7; }
+        if (upload_consts_pairing(C) != cudaSuccess || upload_consts_g2(C) != cudaSuccess || upload_consts_g1(C) != cudaSuccess) { delete ctx; return -7; }
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->devs[0].dev) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -380,7 +199,7 @@ extern "C" void tcb_free(tcb_ctx *ctx) {
 }
 extern "C" const char *tcb_last_error(const tcb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" int tcb_set_engine(tcb_ctx *ctx, int engine) {
-    if (!ctx || (engine != TCB_ENGINE_PAIR && engine != TCB_ENGINE_THREAD)) return -2;
+    if (!ctx || engine != TCB_ENGINE_QUAD) return -2;   // the other engines are debug builds only
     ctx->engine = engine;
     return 0;
 }
@@ -404,7 +223,7 @@ extern "C" int tcb_hash_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const
 }
 extern "C" int tcb_verify_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     DEV_PROLOGUE
-    return impl_verify(ctx, st, n, pk, sig, msgs, off, ok);
+    return impl_verify(ctx, d, st, n, pk, sig, msgs, off, ok);
 }
 extern "C" int tcb_sign_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     DEV_PROLOGUE
@@ -426,7 +245,8 @@ extern "C" int tcb_decrypt_batch_dev(tcb_ctx *ctx, void *stream, size_t n, size_
 }
 extern "C" int tcb_g1_mul_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *sk, const u8 *pts, u8 *out) {
     DEV_PROLOGUE
-    return launch(ctx, st, k_g1_mul, n, n, sk, pts, out);
+    if (n) RUN(run_g1_mul(st, n, sk, pts, out));
+    return 0;
 }
 extern "C" int tcb_commitment_eval_batch_dev(tcb_ctx *ctx, void *stream, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
     DEV_PROLOGUE
@@ -525,7 +345,7 @@ extern "C" int tcb_verify_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 *
         u8 *dpk = up(ctx, d, pk + 96 * s.lo, 96 * cnt), *dsig = up(ctx, d, sig + 192 * s.lo, 192 * cnt);
         u8 *dok = (u8 *)arena_alloc(ctx, d, cnt);
         if (!dpk || !dsig || !dok) return -1;
-        if (impl_verify(ctx, st, cnt, dpk, dsig, dm, doff, dok)) return -1;
+        if (impl_verify(ctx, d, st, cnt, dpk, dsig, dm, doff, dok)) return -1;
         if (down(ctx, d, ok + s.lo, dok, cnt)) return -1;
     END_FOR_EACH_DEV
     return sync_all(ctx);
@@ -602,7 +422,7 @@ static int g1_mul_common(tcb_ctx *ctx, size_t n, const u8 *sk, const u8 *pts, u8
         u8 *dp = pts ? up(ctx, d, pts + 96 * s.lo, 96 * cnt) : nullptr;
         u8 *dout = (u8 *)arena_alloc(ctx, d, 96 * cnt);
         if (!dsk || (pts && !dp) || !dout) return -1;
-        if (launch(ctx, st, k_g1_mul, cnt, cnt, (const u8 *)dsk, (const u8 *)dp, dout)) return -1;
+        RUN(run_g1_mul(st, cnt, dsk, dp, dout));
         if (down(ctx, d, out + 96 * s.lo, dout, 96 * cnt)) return -1;
         CK(cudaMemsetAsync(dsk, 0, 32 * cnt, st));
     END_FOR_EACH_DEV
@@ -635,8 +455,8 @@ extern "C" int tcb_selftest_fp(tcb_ctx *ctx, size_t n, uint64_t seed) {
     CK(cudaMalloc(&bad, 8));
     CK(cudaMemsetAsync(bad, 0, 8, d.stream));
     n = (n + 127) & ~(size_t)127;
-    k_selftest_fp<<<(unsigned)(n / 128), 128, 0, d.stream>>>(n, seed, bad);
-    ctx->launches++;
+    run_selftest(d.stream, n, seed, bad);
+    ctx->launches += 2;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
@@ -670,7 +490,7 @@ extern "C" int tcb_probe_imad(tcb_ctx *ctx, double *macs_per_sec) {
     u64 *out = nullptr;
     CK(cudaMalloc(&out, (size_t)blocks * threads * 8));
     float ms = 0;
-    if (timed(ctx, d, [&] { k_probe_imad<<<blocks, threads, 0, d.stream>>>(out, iters, 12345u); ctx->launches++; }, 3, ms)) return -1;
+    if (timed(ctx, d, [&] { run_probe_imad(d.stream, blocks, threads, out, iters); ctx->launches++; }, 3, ms)) return -1;
     cudaFree(out);
     *macs_per_sec = (double)blocks * threads * iters * 64.0 / (ms * 1e-3);
     return 0;
@@ -680,10 +500,10 @@ extern "C" int tcb_probe_fpmul(tcb_ctx *ctx, double *muls_per_sec) {
     DevState &d = ctx->devs[0];
     CK(cudaSetDevice(d.dev));
     const int blocks = ctx->sm_count * 4, threads = 256, iters = 4096;
-    Fp *out = nullptr;
-    CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(Fp)));
+    void *out = nullptr;
+    CK(cudaMalloc(&out, (size_t)blocks * threads * fp_bytes()));
     float ms = 0;
-    if (timed(ctx, d, [&] { k_probe_fpmul<<<blocks, threads, 0, d.stream>>>(out, iters, 99ULL); ctx->launches++; }, 3, ms)) return -1;
+    if (timed(ctx, d, [&] { run_probe_fpmul(d.stream, blocks, threads, out, iters); ctx->launches++; }, 3, ms)) return -1;
     cudaFree(out);
     *muls_per_sec = (double)blocks * threads * iters * 2.0 / (ms * 1e-3);
     return 0;

@@ -26,10 +26,10 @@ struct Consts {
     Fp g1x, g1y;      // G1 generator
     Fp2c g2x, g2y;    // G2 generator
     Fr fr_r1, fr_r2;  // Fr Montgomery constants
-    // GLV / misc constants can be appended here
+    Fp2c psi_x, psi_y;  // untwist-Frobenius-twist endomorphism: psi(x,y) = (conj(x) psi_x, conj(y) psi_y)
 };
 #if defined(__CUDACC__)
-__device__ __constant__ Consts d_consts;
+static __device__ __constant__ Consts d_consts;   // one copy per translation unit (uploaded by each)
 #endif
 static Consts h_consts;
 TCB_HD const Consts &CONSTS() {
@@ -561,6 +561,66 @@ TCB_HDN Jac<F> jac_mul_jac(const Jac<F> &p, const u32 *k) {
         if ((k[i >> 5] >> (i & 31)) & 1) { acc = started ? jac_add(acc, p) : p; started = true; }
     }
     return acc;
+}
+
+// ----------------------------------------------------------------------------- psi endomorphism and small-scalar multipliers
+template <class F2>
+TCB_HD Jac<F2> jac_psi(const Jac<F2> &p) {
+    const Consts &C = CONSTS();
+    Jac<F2> r;
+    r.x = conj(p.x) * F2::load(C.psi_x);
+    r.y = conj(p.y) * F2::load(C.psi_y);
+    r.z = conj(p.z);
+    return r;
+}
+// |k| * P for a 64-bit constant, Jacobian base (MSB-first double-and-add)
+template <class F>
+TCB_HDN Jac<F> jac_mul_u64(const Jac<F> &p, u64 k) {
+    Jac<F> acc = p;
+    int top = 63;
+    while (top > 0 && !((k >> top) & 1)) top--;
+    for (int i = top - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        if ((k >> i) & 1) acc = jac_add(acc, p);
+    }
+    return acc;
+}
+// sum_j (plus_j - minus_j) 2^j * P, digits given as NAF bit masks
+template <class F>
+TCB_HDN Jac<F> jac_mul_naf64(const Jac<F> &p, u64 plus, u64 minus) {
+    Jac<F> acc = jac_inf<F>();
+    Jac<F> np = jac_neg(p);
+    for (int i = 63; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        if ((plus >> i) & 1) acc = jac_add(acc, p);
+        if ((minus >> i) & 1) acc = jac_add(acc, np);
+    }
+    return acc;
+}
+// Exact multiplication by the G2 cofactor h2 (EXTERNAL pairing scale_by_cofactor) without a
+// 507-bit scalar: with x the (negative) curve parameter and psi the endomorphism,
+//   Q0 = h_eff P = [x^2-x-1]P + [x-1]psi(P) + psi^2(2P)        (Budroni-Pintore, h_eff = 3(x^2-1) h2)
+//   [h2]P = [1/(3(x^2-1)) mod r] Q0,  and on G2 (psi = [x]):  1/(x^2-1) = -x^2,  1/3 = 1 + 2 x^2 (x+1) (x-1)/3
+//   => R = -psi^2(Q0),  T = psi^2(psi(R) + R),  [h2]P = R - [w] T,  w = 2(|x|+1)/3 = 0x8c00aaaaaaab5556.
+// Same group element as the reference's 507-bit double-and-add (checked against it in the tests).
+#define TCB_W_PLUS 0x9001000000000000ULL
+#define TCB_W_MINUS 0x040055555554aaaaULL
+template <class F2>
+TCB_HDN Jac<F2> g2_clear_cofactor(const Aff<F2> &p) {
+    const u64 X = TCB_BLS_X;
+    Jac<F2> pj = jac_from_aff(p);
+    Jac<F2> t1 = jac_neg(jac_mul_u64(pj, X));             // [x]P
+    Jac<F2> t2 = jac_psi(pj);
+    Jac<F2> t3 = jac_psi(jac_psi(jac_dbl(pj)));
+    t3 = jac_add(t3, jac_neg(t2));
+    t2 = jac_add(t1, t2);
+    t2 = jac_neg(jac_mul_u64(t2, X));                      // [x](…)
+    t3 = jac_add(t3, t2);
+    t3 = jac_add(t3, jac_neg(t1));
+    Jac<F2> q0 = jac_add(t3, jac_neg(pj));
+    Jac<F2> r = jac_neg(jac_psi(jac_psi(q0)));
+    Jac<F2> t = jac_psi(jac_psi(jac_add(jac_psi(r), r)));
+    return jac_add(r, jac_neg(jac_mul_naf64(t, TCB_W_PLUS, TCB_W_MINUS)));
 }
 
 // ----------------------------------------------------------------------------- Miller loop (M-type twist, projective lines)
