@@ -3,21 +3,24 @@
 #include "scheme.cuh"
 using namespace tcb;
 typedef Fp2S F2;
+#ifndef TCB_G2_MINB
+#define TCB_G2_MINB 2
+#endif
 
 static __device__ __forceinline__ size_t unit_index() { return ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1; }
-__global__ void __launch_bounds__(128) k_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out) {
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     size_t i = unit_index();
     if (i < n) task_hash_g2<F2>(i, msgs, off, out);
 }
-__global__ void __launch_bounds__(128) k_sign(size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_sign(size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     size_t i = unit_index();
     if (i < n) task_sign<F2>(i, sk, msgs, off, h, out);
 }
-__global__ void __launch_bounds__(128) k_g2_mul_store(size_t units, const u32 *k, const u8 *pts, JacStore<F2> *out, u8 *status, size_t per_item) {
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_mul_store(size_t units, const u32 *k, const u8 *pts, JacStore<F2> *out, u8 *status, size_t per_item) {
     size_t i = unit_index();
     if (i < units) task_g2_mul_store<F2>(i, k, pts, out, status, per_item);
 }
-__global__ void __launch_bounds__(128) k_g2_sum(size_t n, size_t m, const JacStore<F2> *terms, u8 *out) {
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_sum(size_t n, size_t m, const JacStore<F2> *terms, u8 *out) {
     size_t i = unit_index();
     if (i < n) task_g2_sum<F2>(i, m, terms, out);
 }

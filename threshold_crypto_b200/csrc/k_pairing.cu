@@ -4,7 +4,10 @@
 using namespace tcb;
 
 // one item per QUAD of lanes (quad.cuh); h_g2 replaces b_g2 when the hash was computed on device
-__global__ void __launch_bounds__(128, 2) k_verify_g2_quad(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
+#ifndef TCB_QUAD_MINB
+#define TCB_QUAD_MINB 2
+#endif
+__global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_verify_g2_quad(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     if (i >= n) return;
     bool enc_ok;

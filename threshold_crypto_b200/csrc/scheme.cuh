@@ -413,7 +413,7 @@ TCB_HD void task_sign(size_t i, const u8 *sk, const u8 *msgs, const u64 *off, co
     bool ok = true;
     Aff<F2> h = h_g2 ? load_g2<F2>(h_g2 + 192 * i, ok)
                      : jac_to_aff(hash_g2<F2>(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0));
-    store_g2<F2>(out_g2 + 192 * i, jac_to_aff(jac_mul_aff<F2, 8>(h, k)));
+    store_g2<F2>(out_g2 + 192 * i, jac_to_aff(jac_mul_gls4<F2>(h, k)));
 }
 // generic k * P over G2 with the result kept Jacobian in a Montgomery scratch array
 // (used for the per-share terms of interpolate, src/lib.rs:753-765)
@@ -422,7 +422,7 @@ template <class F2>
 TCB_HD void task_g2_mul_store(size_t i, const u32 *k_limbs, const u8 *pts_g2, JacStore<F2> *out, u8 *status, size_t per_item) {
     bool ok = true;
     Aff<F2> p = load_g2<F2>(pts_g2 + 192 * i, ok);
-    Jac<F2> r = jac_mul_aff<F2, 8>(p, k_limbs + 8 * i);
+    Jac<F2> r = jac_mul_gls4<F2>(p, k_limbs + 8 * i);
     r.x.store(out[i].x); r.y.store(out[i].y); r.z.store(out[i].z);
     if (!ok && is_writer<F2>()) status[i / per_item] = 3;
 }
@@ -452,12 +452,12 @@ TCB_HD void task_g1_mul(size_t i, const u8 *sk, const u8 *pts_g1, u8 *out_g1) { 
     Aff<Fp> p;
     if (pts_g1) p = load_g1(pts_g1 + 96 * i, ok);
     else { p.x = CONSTS().g1x; p.y = CONSTS().g1y; p.inf = false; }
-    store_g1(out_g1 + 96 * i, jac_to_aff(jac_mul_aff<Fp, 8>(p, k)));
+    store_g1(out_g1 + 96 * i, jac_to_aff(jac_mul_glv2(p, k)));
 }
 TCB_HD void task_g1_mul_store(size_t i, const u32 *k_limbs, const u8 *pts_g1, Jac1Store *out, u8 *status, size_t per_item) {
     bool ok = true;
     Aff<Fp> p = load_g1(pts_g1 + 96 * i, ok);
-    Jac<Fp> r = jac_mul_aff<Fp, 8>(p, k_limbs + 8 * i);
+    Jac<Fp> r = jac_mul_glv2(p, k_limbs + 8 * i);
     out[i].x = r.x; out[i].y = r.y; out[i].z = r.z;
     if (!ok) status[i / per_item] = 3;
 }
@@ -552,6 +552,34 @@ inline void build_consts(Consts &C) {
     // psi(x, y) = (conj(x) / xi^((p-1)/3), conj(y) / xi^((p-1)/2))
     inv(Fp2::load(C.frob[1][2])).store(C.psi_x);
     inv(Fp2::load(C.frob[1][3])).store(C.psi_y);
+    {   // psi^i coefficients: c_0 = 1, c_{i+1} = conj(c_i) * psi
+        Fp2 cx = Fp2::one(), cy = Fp2::one();
+        for (int i = 0; i < 4; i++) {
+            cx.store(C.psi_cx[i]); cy.store(C.psi_cy[i]);
+            cx = conj(cx) * Fp2::load(C.psi_x); cy = conj(cy) * Fp2::load(C.psi_y);
+        }
+    }
+    h_consts = C;
+    {   // beta: the cube root of unity in Fp with (beta x, y) = [-x^2](x, y) on G1
+        u32 e[12];
+        limbs_from_hex(e, 12, "1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaaa");
+        u64 rem = 0;
+        for (int i = 11; i >= 0; i--) { u64 cur = (rem << 32) | e[i]; e[i] = (u32)(cur / 3); rem = cur % 3; }   // (p - 1) / 3
+        Fp beta = C.r1;
+        for (u32 g = 2; beta == C.r1; g++) {
+            Fp base = Fp::zero();
+            base.l[0] = g;
+            base = fp_to_mont(base);
+            Fp acc = C.r1;
+            for (int i = 383; i >= 0; i--) { acc = sqr(acc); if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * base; }
+            beta = acc;
+        }
+        Aff<Fp> G; G.x = C.g1x; G.y = C.g1y; G.inf = false;
+        const u32 mu[8] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u, 0, 0, 0, 0};   // x^2
+        Aff<Fp> m = jac_to_aff(jac_mul_aff<Fp, 8>(G, mu));       // [x^2] G = -phi(G)
+        if (!(m.x == G.x * beta)) beta = sqr(beta);
+        C.beta = beta;
+    }
     h_consts = C;
 }
 

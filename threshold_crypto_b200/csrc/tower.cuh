@@ -27,6 +27,8 @@ struct Consts {
     Fp2c g2x, g2y;    // G2 generator
     Fr fr_r1, fr_r2;  // Fr Montgomery constants
     Fp2c psi_x, psi_y;  // untwist-Frobenius-twist endomorphism: psi(x,y) = (conj(x) psi_x, conj(y) psi_y)
+    Fp2c psi_cx[4], psi_cy[4];   // psi^i(x,y) = (conj^i(x) psi_cx[i], conj^i(y) psi_cy[i])
+    Fp beta;            // cube root of unity in Fp with (beta x, y) = [-x^2] (x, y) on G1
 };
 #if defined(__CUDACC__)
 static __device__ __constant__ Consts d_consts;   // one copy per translation unit (uploaded by each)
@@ -621,6 +623,176 @@ TCB_HDN Jac<F2> g2_clear_cofactor(const Aff<F2> &p) {
     Jac<F2> r = jac_neg(jac_psi(jac_psi(q0)));
     Jac<F2> t = jac_psi(jac_psi(jac_add(jac_psi(r), r)));
     return jac_add(r, jac_neg(jac_mul_naf64(t, TCB_W_PLUS, TCB_W_MINUS)));
+}
+
+// ----------------------------------------------------------------------------- GLS / GLV scalar multiplication
+// SIMT note: with one scalar per lane (pair), a data-dependent "if (bit) add" diverges across
+// the warp and every bit position ends up paying for an addition.  The multipliers below use
+// *regular* signed recoding (Faz-Hernandez, Longa, Sanchez): every step is one doubling and
+// exactly one table addition, so no slot is wasted.
+//
+// k < 2^256 canonical little-endian limbs.  Returns k mod r in place (at most two subtractions).
+TCB_HD void scalar_reduce(u32 *k) {
+    for (int rep = 0; rep < 2; rep++) {
+        if (limbs_lt_mod<FrParams>(k)) return;
+        u64 bw = 0;
+        for (int i = 0; i < 8; i++) {
+            u64 d = (u64)k[i] - FrParams::mod(i) - bw;
+            k[i] = (u32)d; bw = (d >> 63) & 1;
+        }
+    }
+}
+// q (8 limbs) := q / d, returns q % d, for a 64-bit divisor with its top bit set
+TCB_HD u64 divmod_u64(u32 *q, u64 d) {
+    u64 rem = 0;
+    for (int i = 255; i >= 0; i--) {
+        u32 hi = (u32)(rem >> 63);
+        rem = (rem << 1) | ((q[i >> 5] >> (i & 31)) & 1u);
+        u32 bit = (hi || rem >= d) ? 1u : 0u;
+        if (bit) rem -= d;
+        q[i >> 5] = (q[i >> 5] & ~(1u << (i & 31))) | (bit << (i & 31));
+    }
+    return rem;
+}
+// psi^i applied to an affine point, i in 0..3
+template <class F2>
+TCB_HD Aff<F2> aff_psi_i(const Aff<F2> &p, int i) {
+    const Consts &C = CONSTS();
+    Aff<F2> r;
+    r.inf = p.inf;
+    bool odd = i & 1;
+    r.x = (odd ? conj(p.x) : p.x) * F2::load(C.psi_cx[i]);
+    r.y = (odd ? conj(p.y) : p.y) * F2::load(C.psi_cy[i]);
+    return r;
+}
+// k * P on G2 (P of order r) through the 4-dimensional decomposition k = sum_i d_i X^i,
+// X = |x| = -lambda_psi, i.e. k P = sum_i (-1)^i d_i psi^i(P); 66 doublings + 66 additions from
+// an 8-entry table  T[b3 b2 b1] = P0 + b1 P1 + b2 P2 + b3 P3,  P_i = (-1)^i psi^i(P).
+template <class F2>
+TCB_HDN Jac<F2> jac_mul_gls4(const Aff<F2> &p, const u32 *k_in) {
+    if (p.inf) return jac_inf<F2>();
+    u32 k[8];
+    for (int i = 0; i < 8; i++) k[i] = k_in[i];
+    scalar_reduce(k);
+    u64 a[4];
+    u32 ahi[4] = {0, 0, 0, 0};      // bit 64 of a_i (only a0 + 1 can carry)
+    const u64 X = TCB_BLS_X;
+    a[0] = divmod_u64(k, X);
+    a[1] = divmod_u64(k, X);
+    a[2] = divmod_u64(k, X);
+    a[3] = (u64)k[0] | ((u64)k[1] << 32);        // k < r < X^4  =>  the last quotient fits 64 bits
+    bool even = !(a[0] & 1);
+    if (even) { a[0] += 1; if (a[0] == 0) ahi[0] = 1; }     // make a0 odd; fixed up at the end
+    // table
+    Jac<F2> T[8];
+    Aff<F2> P1 = aff_psi_i(p, 1), P2 = aff_psi_i(p, 2), P3 = aff_psi_i(p, 3);
+    P1.y = -P1.y; P3.y = -P3.y;
+    T[0] = jac_from_aff(p);
+    T[1] = jac_add_mixed(T[0], P1);
+    T[2] = jac_add_mixed(T[0], P2);
+    T[3] = jac_add_mixed(T[1], P2);
+    T[4] = jac_add_mixed(T[0], P3);
+    T[5] = jac_add_mixed(T[1], P3);
+    T[6] = jac_add_mixed(T[2], P3);
+    T[7] = jac_add_mixed(T[3], P3);
+    // regular recoding, digits produced LSB first: sign[j] of a0, idx bits of a1..a3
+    const int L = 65;               // digits 0..L
+    u64 sgn_lo = 0; u32 sgn_hi = 0;   // bit j set  <=>  b0[j] = -1
+    u64 i1_lo = 0, i2_lo = 0, i3_lo = 0; u32 i1_hi = 0, i2_hi = 0, i3_hi = 0;
+    {
+        // b0[j] = 2 * bit_{j+1}(a0) - 1 for j < L, b0[L] = +1
+        u64 a0s = (a[0] >> 1) | ((u64)ahi[0] << 63);       // bits 1..64 of a0 at positions 0..63
+        sgn_lo = ~a0s;                                       // -1 where bit_{j+1} == 0, j = 0..63
+        sgn_hi = 1u;                                         // j = 64: bit 65 of a0 is 0 -> -1 ; j = 65 (top) is +1
+        u64 av[3] = {a[1], a[2], a[3]};
+        u32 avh[3] = {0, 0, 0};
+        u64 *ilo[3] = {&i1_lo, &i2_lo, &i3_lo};
+        u32 *ihi[3] = {&i1_hi, &i2_hi, &i3_hi};
+        for (int j = 0; j <= L; j++) {
+            bool neg = j < 64 ? ((sgn_lo >> j) & 1) : (j == 64 ? (sgn_hi & 1u) : false);
+            for (int t = 0; t < 3; t++) {
+                u32 bit = (u32)(av[t] & 1);
+                if (j < 64) *ilo[t] |= (u64)bit << j; else *ihi[t] |= bit << (j - 64);
+                // a = floor(a / 2) - floor(b / 2),  b = bit * (+1 | -1):  b = -1 -> floor(-1/2) = -1 -> +1
+                av[t] = (av[t] >> 1) | ((u64)avh[t] << 63);
+                avh[t] = 0;
+                if (bit && neg && j < L) { av[t] += 1; if (av[t] == 0) avh[t] = 1; }
+            }
+        }
+    }
+    Jac<F2> acc = jac_inf<F2>();
+    for (int j = L; j >= 0; j--) {
+        acc = jac_dbl(acc);
+        bool neg = j < 64 ? ((sgn_lo >> j) & 1) : (j == 64 ? (sgn_hi & 1u) : false);
+        u32 b1 = j < 64 ? (u32)((i1_lo >> j) & 1) : ((i1_hi >> (j - 64)) & 1u);
+        u32 b2 = j < 64 ? (u32)((i2_lo >> j) & 1) : ((i2_hi >> (j - 64)) & 1u);
+        u32 b3 = j < 64 ? (u32)((i3_lo >> j) & 1) : ((i3_hi >> (j - 64)) & 1u);
+        Jac<F2> t = T[b1 | (b2 << 1) | (b3 << 2)];
+        if (neg) t.y = -t.y;
+        acc = jac_add(acc, t);
+    }
+    if (even) { Aff<F2> np = p; np.y = -p.y; acc = jac_add_mixed(acc, np); }
+    return acc;
+}
+// q (8 limbs) := q / d for a 128-bit divisor d = (dhi, dlo) with its top bit set; remainder in (rhi, rlo)
+TCB_HD void divmod_u128(u32 *q, u64 dhi, u64 dlo, u64 &rhi, u64 &rlo) {
+    rhi = 0; rlo = 0;
+    for (int i = 255; i >= 0; i--) {
+        u32 carry = (u32)(rhi >> 63);
+        rhi = (rhi << 1) | (rlo >> 63);
+        rlo = (rlo << 1) | ((q[i >> 5] >> (i & 31)) & 1u);
+        bool ge = carry || rhi > dhi || (rhi == dhi && rlo >= dlo);
+        if (ge) { u64 b = rlo < dlo; rlo -= dlo; rhi = rhi - dhi - b; }
+        q[i >> 5] = (q[i >> 5] & ~(1u << (i & 31))) | ((ge ? 1u : 0u) << (i & 31));
+    }
+}
+// k * P on G1 (P of order r): k = a + b X^2 and [X^2]P = -phi(P), phi(x, y) = (beta x, y);
+// regular recoding on (a, b): 130 doublings + 130 additions from {P0, P0 + P1}, P1 = -phi(P).
+TCB_HDN Jac<Fp> jac_mul_glv2(const Aff<Fp> &p, const u32 *k_in) {
+    if (p.inf) return jac_inf<Fp>();
+    u32 k[8];
+    for (int i = 0; i < 8; i++) k[i] = k_in[i];
+    scalar_reduce(k);
+    // X^2 = 0xac45a4010001a402 0000000100000000 (128 bit, top bit set)
+    const u64 MU_HI = 0xac45a4010001a402ULL, MU_LO = 0x0000000100000000ULL;
+    u64 ahi, alo;
+    divmod_u128(k, MU_HI, MU_LO, ahi, alo);
+    u64 blo = (u64)k[0] | ((u64)k[1] << 32), bhi = (u64)k[2] | ((u64)k[3] << 32);
+    bool even = !(alo & 1);
+    u32 atop = 0;
+    if (even) { alo += 1; if (alo == 0) { ahi += 1; if (ahi == 0) atop = 1; } }
+    Aff<Fp> P1;
+    P1.x = p.x * CONSTS().beta; P1.y = -p.y; P1.inf = false;
+    Jac<Fp> T0 = jac_from_aff(p);
+    Jac<Fp> T1 = jac_add_mixed(T0, P1);
+    const int L = 129;   // digits 0..L
+    // sign bits (b0[j] = -1) and index bits for j = 0..L, in three words
+    u64 sg[3] = {0, 0, 0}, ix[3] = {0, 0, 0};
+    {
+        // bits 1..129 of a at positions 0..128
+        u64 s0 = (alo >> 1) | (ahi << 63), s1 = (ahi >> 1) | ((u64)atop << 63);
+        sg[0] = ~s0; sg[1] = ~s1; sg[2] = 1u;      // j = 128: bit 129 of a is 0 -> -1 ; j = 129 (top) is +1
+        u64 b0 = blo, b1 = bhi; u32 b2 = 0;
+        for (int j = 0; j <= L; j++) {
+            bool neg = (sg[j >> 6] >> (j & 63)) & 1;
+            if (j == L) neg = false;
+            u32 bit = (u32)(b0 & 1);
+            ix[j >> 6] |= (u64)bit << (j & 63);
+            b0 = (b0 >> 1) | (b1 << 63); b1 = (b1 >> 1) | ((u64)b2 << 63); b2 = 0;
+            if (bit && neg && j < L) { b0 += 1; if (b0 == 0) { b1 += 1; if (b1 == 0) b2 = 1; } }
+        }
+    }
+    Jac<Fp> acc = jac_inf<Fp>();
+    for (int j = L; j >= 0; j--) {
+        acc = jac_dbl(acc);
+        bool neg = (j < L) && ((sg[j >> 6] >> (j & 63)) & 1);
+        bool one = (ix[j >> 6] >> (j & 63)) & 1;
+        Jac<Fp> t = one ? T1 : T0;
+        if (neg) t.y = -t.y;
+        acc = jac_add(acc, t);
+    }
+    if (even) { Aff<Fp> np = p; np.y = -p.y; acc = jac_add_mixed(acc, np); }
+    return acc;
 }
 
 // ----------------------------------------------------------------------------- Miller loop (M-type twist, projective lines)
