@@ -57,6 +57,10 @@ int tcb_verify_g2_batch(tcb_ctx *, size_t n, const uint8_t *a_g1, const uint8_t 
                         const uint8_t *c_g1, const uint8_t *d_g2, uint8_t *ok);
 /* hash_g2 (src/lib.rs:691-694) */
 int tcb_hash_g2_batch(tcb_ctx *, size_t n, const uint8_t *msgs, const uint64_t *off, uint8_t *out_g2);
+/* hash_g1_g2 (src/lib.rs:697-707): H(msg-or-its-SHA3 || compressed(g1)); used by
+ * Ciphertext::verify and verify_decryption_share together with tcb_verify_g2_batch */
+int tcb_hash_g1_g2_batch(tcb_ctx *, size_t n, const uint8_t *g1, const uint8_t *msgs, const uint64_t *off,
+                         uint8_t *out_g2);
 /* PublicKey::verify / PublicKeyShare::verify (src/lib.rs:115-117,177-179) */
 int tcb_verify_batch(tcb_ctx *, size_t n, const uint8_t *pk_g1, const uint8_t *sig_g2,
                      const uint8_t *msgs, const uint64_t *off, uint8_t *ok);

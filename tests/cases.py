@@ -68,6 +68,9 @@ def check_all(E, O, n_sig=6, n_comb=3, t=3, deg=6, n_eval=5, seed=7):
     h = O.hash_g2_batch(msgs)
     assert np.array_equal(E.hash_g2_batch(msgs), h)
     assert np.array_equal(E.g1_mul_gen_batch(sk), O.g1_mul_gen_batch(sk))
+    long_msgs = [m * (1 + 9 * (k % 2)) for k, m in enumerate(msgs)]          # some > 64 bytes (hashed first), some short
+    exp_hg = np.stack([O.hash_g1_g2(pk[k], long_msgs[k]) for k in range(n_sig)])
+    assert np.array_equal(E.hash_g1_g2_batch(pk, long_msgs), exp_hg)
     assert np.array_equal(E.sign_batch(sk, msgs), O.sign_batch(sk, msgs))
     assert np.array_equal(E.sign_g2_batch(sk, h), O.sign_g2_batch(sk, h))
     exp = O.verify_batch(pk, sig, msgs)

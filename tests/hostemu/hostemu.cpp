@@ -29,6 +29,10 @@ extern "C" int tcb_hash_g2_batch(tcb_ctx *, size_t n, const u8 *msgs, const u64 
     for (size_t i = 0; i < n; i++) task_hash_g2<Fp2>(i, msgs, off, out);
     return 0;
 }
+extern "C" int tcb_hash_g1_g2_batch(tcb_ctx *, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
+    for (size_t i = 0; i < n; i++) task_hash_g1_g2<Fp2>(i, g1, msgs, off, out);
+    return 0;
+}
 extern "C" int tcb_verify_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     for (size_t i = 0; i < n; i++) task_verify<Fp2>(i, pk, sig, msgs, off, ok);
     return 0;

@@ -73,7 +73,12 @@ def test_threshold_enc_decrypt_roundtrip(tc, O):     # src/lib.rs:908-939 (encry
     r32 = tc._fr(0x1234567890abcdef1234567890abcdef)
     u, v, w = O.encrypt(pk_set.public_key().raw, r32, msg)
     ct = tc.Ciphertext(u, v, w)
+    assert ct.verify()                                            # src/lib.rs:508-512
+    assert not tc.Ciphertext(u, v + b"x", w).verify()             # tampered body (src/lib.rs:893-896)
     shares = {i: sk_set.secret_key_share(i).decrypt_share_no_verify(ct) for i in (8, 5, 9)}
+    for i, s in shares.items():
+        assert pk_set.public_key_share(i).verify_decryption_share(s, ct)
+    assert not pk_set.public_key_share(5).verify_decryption_share(shares[8], ct)
     assert pk_set.decrypt(shares, ct) == msg
     with pytest.raises(tc.NotEnoughShares):
         pk_set.decrypt({8: shares[8], 5: shares[5]}, ct)

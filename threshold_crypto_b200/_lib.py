@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "csrc", "libtcb200.so")
+# TCB200_LIB selects an experiment build of the SAME CUDA library (e.g. another launch-bounds variant)
+DEFAULT_LIB = os.environ.get("TCB200_LIB") or os.path.join(_HERE, "csrc", "libtcb200.so")
 
 ENGINE_PAIR = 0
 ENGINE_THREAD = 1
@@ -96,6 +97,13 @@ class Engine:
         buf, off = pack_msgs(msgs)
         out = np.zeros((len(msgs), 192), np.uint8)
         self._ck(self.lib.tcb_hash_g2_batch(self.ctx, C.c_size_t(len(msgs)), _p(buf), _p(off), _p(out)))
+        return out
+
+    def hash_g1_g2_batch(self, g1, msgs):
+        g = _u8(g1)
+        buf, off = pack_msgs(msgs)
+        out = np.zeros((len(msgs), 192), np.uint8)
+        self._ck(self.lib.tcb_hash_g1_g2_batch(self.ctx, C.c_size_t(len(msgs)), _p(g), _p(buf), _p(off), _p(out)))
         return out
 
     def verify_batch(self, pk_g1, sig_g2, msgs):

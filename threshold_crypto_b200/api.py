@@ -102,12 +102,18 @@ class PublicKey(_Point):           # PublicKey(G1), src/lib.rs:79
 class PublicKeyShare(PublicKey):   # src/lib.rs:160
 
     def verify_decryption_share(self, share, ct):      # src/lib.rs:182-186: e(share, H(U,V)) == e(pk_i, W)
-        raise NotImplementedError("needs hash_g1_g2 through the ABI (SURVEY §8f row 2)")
+        h = engine().hash_g1_g2_batch(ct.u, [ct.v])
+        return bool(engine().verify_g2_batch(share.raw, h[0], self.raw, ct.w)[0])
 
 
 class Ciphertext:                  # Ciphertext(G1, Vec<u8>, G2), src/lib.rs:474-478
     def __init__(self, u, v, w):
         self.u, self.v, self.w = np.asarray(u, np.uint8), bytes(v), np.asarray(w, np.uint8)
+
+    def verify(self):                                  # src/lib.rs:508-512: e(g1, W) == e(U, H(U,V))
+        h = engine().hash_g1_g2_batch(self.u, [self.v])
+        # (a, b, c, d) = (U, H, g1, W): e(U, H) == e(g1, W)
+        return bool(engine().verify_g2_batch(self.u, h[0], None, self.w)[0])
 
 
 class SecretKey:                   # SecretKey(Fr), src/lib.rs:302

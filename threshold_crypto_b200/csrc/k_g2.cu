@@ -1,4 +1,8 @@
 // k_g2.cu — G2 kernels on the lane-pair engine (Fp2S): hash_g2, sign, per-share terms and sums.
+// The sliced Fp2 multiply / square are real functions in this translation unit: with them inlined
+// the hash kernel spent 61% of its stall samples on instruction fetch (profiles/r1d_*), as functions
+// k_hash_g2 runs 2x faster.  (The quad pairing kernel in k_pairing.cu prefers them inlined.)
+#define TCB_FP2S_NOINLINE 1
 #include "kern.h"
 #include "scheme.cuh"
 using namespace tcb;
@@ -11,6 +15,10 @@ static __device__ __forceinline__ size_t unit_index() { return ((size_t)blockIdx
 __global__ void __launch_bounds__(128, TCB_G2_MINB) k_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     size_t i = unit_index();
     if (i < n) task_hash_g2<F2>(i, msgs, off, out);
+}
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_hash_g1_g2(size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
+    size_t i = unit_index();
+    if (i < n) task_hash_g1_g2<F2>(i, g1, msgs, off, out);
 }
 __global__ void __launch_bounds__(128, TCB_G2_MINB) k_sign(size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     size_t i = unit_index();
@@ -29,6 +37,9 @@ static inline unsigned grid2(size_t units) { return (unsigned)((units * 2 + 127)
 cudaError_t upload_consts_g2(const Consts &c) { return cudaMemcpyToSymbol(d_consts, &c, sizeof c); }
 void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     if (n) k_hash_g2<<<grid2(n), 128, 0, st>>>(n, msgs, off, out);
+}
+void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
+    if (n) k_hash_g1_g2<<<grid2(n), 128, 0, st>>>(n, g1, msgs, off, out);
 }
 void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     if (n) k_sign<<<grid2(n), 128, 0, st>>>(n, sk, msgs, off, h, out);

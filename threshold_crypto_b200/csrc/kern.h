@@ -20,6 +20,7 @@ void run_selftest(cudaStream_t st, size_t n, u64 seed, unsigned long long *bad);
 // ---- k_g2.cu  (lane-pair engine)
 cudaError_t upload_consts_g2(const tcb::Consts &c);
 void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out);
+void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out);
 void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out);
 size_t g2_term_bytes();
 void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item);

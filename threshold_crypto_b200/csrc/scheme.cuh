@@ -393,6 +393,14 @@ TCB_HD void task_hash_g2(size_t i, const u8 *msgs, const u64 *off, u8 *out_g2) {
     Jac<F2> h = hash_g2<F2>(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0);
     store_g2<F2>(out_g2 + 192 * i, jac_to_aff(h));
 }
+// a2: hash_g1_g2 (src/lib.rs:697-707) -> uncompressed affine G2
+template <class F2>
+TCB_HD void task_hash_g1_g2(size_t i, const u8 *g1_pts, const u8 *msgs, const u64 *off, u8 *out_g2) {
+    bool ok = true;
+    Aff<Fp> g = load_g1(g1_pts + 96 * i, ok);
+    Jac<F2> h = hash_g1_g2<F2>(g, msgs + off[i], (size_t)(off[i + 1] - off[i]));
+    store_g2<F2>(out_g2 + 192 * i, jac_to_aff(h));
+}
 // a3: PublicKey::verify = hash_g2 then a1 (src/lib.rs:115-117)
 template <class F2>
 TCB_HD void task_verify(size_t i, const u8 *pk_g1, const u8 *sig_g2, const u8 *msgs, const u64 *off, u8 *ok_out) {

@@ -335,6 +335,21 @@ extern "C" int tcb_hash_g2_batch(tcb_ctx *ctx, size_t n, const u8 *msgs, const u
     END_FOR_EACH_DEV
     return sync_all(ctx);
 }
+extern "C" int tcb_hash_g1_g2_batch(tcb_ctx *ctx, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
+    HOST_PROLOGUE
+    std::vector<std::vector<u64>> keep;
+    keep.reserve(G);
+    FOR_EACH_DEV
+        u8 *dm; u64 *doff;
+        if (up_msgs(ctx, d, msgs, off, s.lo, s.hi, keep, dm, doff)) return -1;
+        u8 *dg = up(ctx, d, g1 + 96 * s.lo, 96 * cnt);
+        u8 *dout = (u8 *)arena_alloc(ctx, d, 192 * cnt);
+        if (!dg || !dout) return -1;
+        RUN(run_hash_g1_g2(st, cnt, dg, dm, doff, dout));
+        if (down(ctx, d, out + 192 * s.lo, dout, 192 * cnt)) return -1;
+    END_FOR_EACH_DEV
+    return sync_all(ctx);
+}
 extern "C" int tcb_verify_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     HOST_PROLOGUE
     std::vector<std::vector<u64>> keep;

@@ -164,7 +164,14 @@ TCB_D Fp2S operator-(const Fp2S &a, const Fp2S &b) { Fp2S r; r.h = a.h - b.h; re
 TCB_D Fp2S operator-(const Fp2S &a) { Fp2S r; r.h = -a.h; return r; }
 TCB_D Fp2S dbl(const Fp2S &a) { Fp2S r; r.h = dbl(a.h); return r; }
 TCB_D Fp2S conj(const Fp2S &a) { Fp2S r; r.h = lane_role() ? -a.h : a.h; return r; }
-TCB_D Fp2S operator*(const Fp2S &a, const Fp2S &b) {
+// TCB_FP2S_CALL: build the sliced multiply / square as real functions instead of inlining them at
+// every use (hot-loop code size vs. call overhead; see DESIGN.md "instruction footprint").
+#if defined(TCB_FP2S_NOINLINE)
+#define TCB_FP2S_CALL static __device__ __noinline__
+#else
+#define TCB_FP2S_CALL TCB_D
+#endif
+TCB_FP2S_CALL Fp2S operator*(const Fp2S &a, const Fp2S &b) {
     Fp oa = partner(a.h), ob = partner(b.h);
     bool role = lane_role();
     // role 0: a0*b0 + a1*(-b1) = h_a*h_b + o_a*(-o_b);  role 1: a0*b1 + a1*b0 = o_a*h_b + h_a*o_b
@@ -173,7 +180,7 @@ TCB_D Fp2S operator*(const Fp2S &a, const Fp2S &b) {
     Fp2S r; r.h = dot2(a.h, y1, oa, y2);
     return r;
 }
-TCB_D Fp2S sqr(const Fp2S &a) {
+TCB_FP2S_CALL Fp2S sqr(const Fp2S &a) {
     Fp o = partner(a.h);
     bool role = lane_role();
     // role 0: (a0 + a1)(a0 - a1);  role 1: (2 a0) a1
