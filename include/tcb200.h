@@ -87,6 +87,15 @@ int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const uint8_t *coeff_g1, si
 /* SecretKey::public_key / Poly::commitment (src/lib.rs:367-369, src/poly.rs:372-377): g1 * c */
 int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const uint8_t *sk, uint8_t *out_g1);
 
+/* SURVEY §8(f) row 1 — batched wire-format codecs.  Compressed encodings of SURVEY App. B (48 B / 96 B);
+ * decompression is the CHECKED decode of PublicKey::from_bytes / Signature::from_bytes
+ * (src/lib.rs:140-146,246-252) and serde `projective::deserialize` (src/serde_impl.rs:187-218):
+ * flags, x < p, on the curve and in the r-order subgroup; status[i] = 0 ok | 3 invalid. */
+int tcb_g1_compress_batch(tcb_ctx *, size_t n, const uint8_t *unc_g1, uint8_t *out48);
+int tcb_g2_compress_batch(tcb_ctx *, size_t n, const uint8_t *unc_g2, uint8_t *out96);
+int tcb_g1_decompress_batch(tcb_ctx *, size_t n, const uint8_t *in48, uint8_t *out_g1, uint8_t *status);
+int tcb_g2_decompress_batch(tcb_ctx *, size_t n, const uint8_t *in96, uint8_t *out_g2, uint8_t *status);
+
 /* Device-resident variants (inputs/outputs in HBM of ctx's first device; enqueue only). */
 int tcb_verify_g2_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *a_g1, const uint8_t *b_g2,
                             const uint8_t *c_g1, const uint8_t *d_g2, uint8_t *ok);

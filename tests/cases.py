@@ -154,3 +154,34 @@ def check_edges(E, O):
     dec, st = E.decrypt_batch(2, 1, xs, sh, vs)
     odec, _ = O.decrypt_batch(2, 1, xs, sh, vs)
     assert dec == odec
+
+
+def check_codecs(E, O, golden=None, seed=9, n=6):
+    """compress / checked decompress against the oracle, incl. infinity and the
+    invalid encodings (x >= p, off-curve, wrong flags, on-curve-but-not-in-subgroup)."""
+    rng = np.random.default_rng(seed)
+    sk = rand_fr(rng, n)
+    p1 = np.concatenate([O.g1_mul_gen_batch(sk), INF1[None, :]])
+    p2 = np.concatenate([O.sign_g2_batch(sk, np.tile(O.g2_generator(), (n, 1))), INF2[None, :]])
+    c1, c2 = O.g1_compress(p1), O.g2_compress(p2)
+    assert np.array_equal(E.g1_compress_batch(p1), c1)
+    assert np.array_equal(E.g2_compress_batch(p2), c2)
+    u1, s1 = E.g1_decompress_batch(c1)
+    u2, s2 = E.g2_decompress_batch(c2)
+    assert not s1.any() and not s2.any() and np.array_equal(u1, p1) and np.array_equal(u2, p2)
+    # tampered encodings: every variant must get the oracle's verdict and output
+    bad1 = c1.copy(); bad1[0, 47] ^= 1; bad1[1, 0] &= 0x7f; bad1[2, 0] |= 0x1f; bad1[2, 1:] = 0xff; bad1[3, 0] ^= 0x20
+    bad2 = c2.copy(); bad2[0, 95] ^= 1; bad2[1, 0] &= 0x7f; bad2[2, 60] ^= 0x80; bad2[3, 0] ^= 0x20; bad2[4, 48] = 0xff; bad2[4, 49:96] = 0xff
+    for bad, dec_e, dec_o in ((bad1, E.g1_decompress_batch, O.g1_decompress), (bad2, E.g2_decompress_batch, O.g2_decompress)):
+        ue, se = dec_e(bad)
+        uo, so = dec_o(bad)
+        assert np.array_equal(se, so), (se, so)
+        assert np.array_equal(ue[so == 0], uo[so == 0])
+    if golden is not None:
+        from conftest import hxs
+        u, s = E.g1_decompress_batch(hxs(golden["g1_bad_compressed"]))
+        assert list(s) == [3] * len(s)
+        u, s = E.g1_decompress_batch(hxs(golden["pk_compressed"]))
+        assert not s.any() and [bytes(x).hex() for x in u] == golden["pk"]
+        u, s = E.g2_decompress_batch(hxs(golden["hash_g2_compressed"]))
+        assert not s.any() and [bytes(x).hex() for x in u] == golden["hash_g2"]

@@ -97,4 +97,51 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff,
     return 0;
 }
 
+extern "C" int tcb_g1_compress_batch(tcb_ctx *, size_t n, const u8 *unc, u8 *out) { for (size_t i = 0; i < n; i++) task_g1_compress(i, unc, out); return 0; }
+extern "C" int tcb_g2_compress_batch(tcb_ctx *, size_t n, const u8 *unc, u8 *out) { for (size_t i = 0; i < n; i++) task_g2_compress<Fp2>(i, unc, out); return 0; }
+extern "C" int tcb_g1_decompress_batch(tcb_ctx *, size_t n, const u8 *in, u8 *out, u8 *st) { for (size_t i = 0; i < n; i++) task_g1_decompress(i, in, out, st); return 0; }
+extern "C" int tcb_g2_decompress_batch(tcb_ctx *, size_t n, const u8 *in, u8 *out, u8 *st) { for (size_t i = 0; i < n; i++) task_g2_decompress<Fp2>(i, in, out, st); return 0; }
 extern "C" uint64_t tcb_emu_mac_count(int reset) { uint64_t v = g_mac_count; if (reset) g_mac_count = 0; return v; }
+
+// test hook: number of mismatches between the binary-GCD inverse and the Fermat inverse on n
+// pseudo-random elements plus the edge values 0, 1, p-1
+extern "C" int tcb_emu_inv_check(int n, uint64_t seed) {
+    ensure();
+    int bad = 0;
+    for (int i = 0; i < n + 3; i++) {
+        Fp a;
+        for (;;) {
+            for (int k = 0; k < 12; k++) { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; a.l[k] = (u32)(seed >> 32); }
+            a.l[11] &= 0x1fffffffu;
+            if (limbs_lt_mod<FpParams>(a.l)) break;
+        }
+        if (i == n) a = Fp::zero();
+        if (i == n + 1) a = fp_one();
+        if (i == n + 2) a = -fp_one();
+        Fp x = fp_inv(a), y = fp_inv_fermat(a);
+        if (x != y) bad++;
+        if (i < n && (x * a) != fp_one()) bad++;
+    }
+    return bad;
+}
+
+extern "C" int tcb_emu_issquare_check(int n, uint64_t seed) {
+    ensure();
+    int bad = 0, squares = 0;
+    for (int i = 0; i < n + 3; i++) {
+        Fp a;
+        for (;;) {
+            for (int k = 0; k < 12; k++) { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; a.l[k] = (u32)(seed >> 32); }
+            a.l[11] &= 0x1fffffffu;
+            if (limbs_lt_mod<FpParams>(a.l)) break;
+        }
+        if (i == n) a = Fp::zero();
+        if (i == n + 1) a = fp_one();
+        if (i == n + 2) a = -fp_one();          // -1 is a non-residue (p = 3 mod 4)
+        Fp s = fp_pow<ExpPp1d4>(a);
+        bool want = sqr(s) == a;
+        if (fp_is_square(a) != want) bad++;
+        squares += want;
+    }
+    return bad * 100000 + squares;
+}

@@ -144,3 +144,7 @@ def test_multi_device_ctx_matches_single(O):
     out, st = E.combine_g2_batch(7, 3, xs, sh)
     assert np.array_equal(out, master)
     E.close()
+
+
+def test_codecs(gpu_engine, O, golden):
+    cases.check_codecs(gpu_engine, O, golden, n=40)

@@ -33,3 +33,17 @@ def test_hostemu_golden(emu, golden):
     ce = golden["commit_eval"]
     out = emu.commitment_eval_batch(hxs(ce["coeff"]), np.concatenate([hx(x) for x in ce["x"]]))
     assert [bytes(p).hex() for p in out] == ce["out"]
+
+
+def test_binary_gcd_inverse_and_legendre_symbol(emu):
+    """fp_inv (branch-free binary GCD) == Fermat inverse, fp_is_square (binary Jacobi) == Euler
+    criterion, on random elements and the edge values 0, 1, p-1 (host instantiation of tower.cuh)."""
+    import ctypes as C
+    lib = emu.lib
+    assert lib.tcb_emu_inv_check(500, C.c_uint64(99)) == 0
+    r = lib.tcb_emu_issquare_check(1000, C.c_uint64(98))
+    assert r // 100000 == 0 and 400 < r % 100000 < 620
+
+
+def test_hostemu_codecs(emu, O, golden):
+    cases.check_codecs(emu, O, golden)

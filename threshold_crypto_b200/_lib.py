@@ -173,6 +173,30 @@ class Engine:
         self._ck(self.lib.tcb_g1_mul_gen_batch(self.ctx, C.c_size_t(n), _p(sk), _p(out)))
         return out
 
+    # ---- wire-format codecs
+    def _codec(self, name, data, in_w, out_w, with_status):
+        a = _u8(data)
+        n = a.size // in_w
+        out = np.zeros((n, out_w), np.uint8)
+        if with_status:
+            st = np.zeros(n, np.uint8)
+            self._ck(getattr(self.lib, name)(self.ctx, C.c_size_t(n), _p(a), _p(out), _p(st)))
+            return out, st
+        self._ck(getattr(self.lib, name)(self.ctx, C.c_size_t(n), _p(a), _p(out)))
+        return out
+
+    def g1_compress_batch(self, unc):
+        return self._codec("tcb_g1_compress_batch", unc, 96, 48, False)
+
+    def g2_compress_batch(self, unc):
+        return self._codec("tcb_g2_compress_batch", unc, 192, 96, False)
+
+    def g1_decompress_batch(self, comp):
+        return self._codec("tcb_g1_decompress_batch", comp, 48, 96, True)
+
+    def g2_decompress_batch(self, comp):
+        return self._codec("tcb_g2_decompress_batch", comp, 96, 192, True)
+
     # ---- self-test / probes (CUDA library only)
     def selftest_fp(self, n=1 << 16, seed=1):
         rc = self.lib.tcb_selftest_fp(self.ctx, C.c_size_t(n), C.c_uint64(seed))

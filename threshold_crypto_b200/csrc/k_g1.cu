@@ -87,6 +87,14 @@ __global__ void __launch_bounds__(256) k_probe_fpmul(Fp *out, int iters, u64 see
 }
 
 
+__global__ void __launch_bounds__(128) k_g1_compress(size_t n, const u8 *unc, u8 *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_g1_compress(i, unc, out);
+}
+__global__ void __launch_bounds__(128) k_g1_decompress(size_t n, const u8 *in, u8 *out, u8 *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_g1_decompress(i, in, out, status);
+}
 namespace tcbk {
 static inline unsigned grid1(size_t n) { return (unsigned)((n + 127) / 128); }
 cudaError_t upload_consts_g1(const Consts &c) { return cudaMemcpyToSymbol(d_consts, &c, sizeof c); }
@@ -113,6 +121,8 @@ void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab) {
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out) {
     if (n) k_commit_eval<<<grid1(n), 128, 0, st>>>(n, deg, (const Jac1Store *)tab, x, out);
 }
+void run_g1_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out) { if (n) k_g1_compress<<<grid1(n), 128, 0, st>>>(n, unc, out); }
+void run_g1_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status) { if (n) k_g1_decompress<<<grid1(n), 128, 0, st>>>(n, in, out, status); }
 void run_probe_imad(cudaStream_t st, int blocks, int threads, u64 *out, int iters) { k_probe_imad<<<blocks, threads, 0, st>>>(out, iters, 12345u); }
 void run_probe_fpmul(cudaStream_t st, int blocks, int threads, void *out, int iters) { k_probe_fpmul<<<blocks, threads, 0, st>>>((Fp *)out, iters, 99ULL); }
 }  // namespace tcbk

@@ -32,6 +32,14 @@ __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_sum(size_t n, size_t m,
     size_t i = unit_index();
     if (i < n) task_g2_sum<F2>(i, m, terms, out);
 }
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_compress(size_t n, const u8 *unc, u8 *out) {
+    size_t i = unit_index();
+    if (i < n) task_g2_compress<F2>(i, unc, out);
+}
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_decompress(size_t n, const u8 *in, u8 *out, u8 *status) {
+    size_t i = unit_index();
+    if (i < n) task_g2_decompress<F2>(i, in, out, status);
+}
 namespace tcbk {
 static inline unsigned grid2(size_t units) { return (unsigned)((units * 2 + 127) / 128); }
 cudaError_t upload_consts_g2(const Consts &c) { return cudaMemcpyToSymbol(d_consts, &c, sizeof c); }
@@ -44,6 +52,8 @@ void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, con
 void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     if (n) k_sign<<<grid2(n), 128, 0, st>>>(n, sk, msgs, off, h, out);
 }
+void run_g2_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out) { if (n) k_g2_compress<<<grid2(n), 128, 0, st>>>(n, unc, out); }
+void run_g2_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status) { if (n) k_g2_decompress<<<grid2(n), 128, 0, st>>>(n, in, out, status); }
 size_t g2_term_bytes() { return sizeof(JacStore<F2>); }
 void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item) {
     if (units) k_g2_mul_store<<<grid2(units), 128, 0, st>>>(units, k, pts, (JacStore<F2> *)terms, status, per_item);

@@ -47,6 +47,13 @@ __global__ void k_selftest_fp(size_t n, u64 seed, unsigned long long *bad) {
     if (((a + b) - b) != a) errs++;
     if (!(a + (-a)).is_zero()) errs++;
     if (!limbs_lt_mod<FpParams>((a + b).l) || !limbs_lt_mod<FpParams>((a - b).l) || !limbs_lt_mod<FpParams>(d2.l)) errs++;
+    if (((i >> 5) & 15) == 0) {   // warp-uniform subset: binary-GCD inverse and Legendre symbol against the Fermat / Euler powers
+        Fp am = fp_to_mont(a);
+        if (fp_inv(am) != fp_inv_fermat(am)) errs++;
+        Fp rt = fp_pow<ExpPp1d4>(am);
+        if (fp_is_square(am) != (sqr(rt) == am)) errs++;
+        if (fp_half(am) + fp_half(am) != am) errs++;
+    }
     // sliced Fp2 against scalar Fp2: lanes of a pair share (a,b,c,d) of the even lane
     {
         u32 m = 3u << (threadIdx.x & 30u);

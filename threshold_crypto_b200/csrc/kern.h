@@ -22,6 +22,8 @@ cudaError_t upload_consts_g2(const tcb::Consts &c);
 void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out);
 void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out);
 void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out);
+void run_g2_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out);
+void run_g2_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status);
 size_t g2_term_bytes();
 void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item);
 void run_g2_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out);
@@ -35,6 +37,8 @@ void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out)
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);
+void run_g1_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out);
+void run_g1_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status);
 void run_probe_imad(cudaStream_t st, int blocks, int threads, u64 *out, int iters);
 void run_probe_fpmul(cudaStream_t st, int blocks, int threads, void *out, int iters);
 size_t fp_bytes();

@@ -195,6 +195,13 @@ TCB_HD Fp fp_random(ChaChaRng &g) {
 }
 // ---- helpers that make the sampling loop work for both engines (1 or 2 lanes per item)
 template <class F2>
+TCB_HD bool unit_and(bool v) {   // AND over the lanes of the unit
+#if defined(__CUDA_ARCH__)
+    if (F2::SLICED) return pair_and(v);
+#endif
+    return v;
+}
+template <class F2>
 TCB_HD int vote_first(bool ok_me) {   // lowest lane of the unit whose flag is set, or -1 (uniform over the unit)
 #if defined(__CUDA_ARCH__)
     if (F2::SLICED) {
@@ -246,8 +253,9 @@ TCB_HD Fp fp_half(const Fp &a) {
 // no root / zero.  The candidates are consumed from the ChaCha stream in the reference's order;
 // HOW a candidate is tested and the root extracted is free (any root gives the same point after
 // the ordering rule):
-//   * residuosity + first half of the square root: s = sqrt(norm(a)) in Fp by one Fp power;
-//     an engine with two lanes per item tests two consecutive candidates per round;
+//   * residuosity by the Legendre symbol of norm(a) (binary Jacobi algorithm on the ALU pipe, no
+//     multiplications); an engine with two lanes per item tests two consecutive candidates per
+//     round; only the winning candidate pays for s = sqrt(norm(a)) (one Fp power);
 //   * y0 = sqrt((a0 +- s)/2), y1 = a1 / (2 y0) with e = delta^((p-3)/4): y0 = delta e, 1/y0 = e;
 //     the two lanes try the two signs at once;
 //   * the cofactor multiplication runs AFTER the rejection loop (all lanes converged) and uses
@@ -275,12 +283,11 @@ TCB_HDN Jac<F2> g2_random(ChaChaRng &g) {
             }
             Fp2 ac = sqr(xc) * xc + b2;
             Fp nrm = norm(ac);
-            Fp sc = fp_pow<ExpPp1d4>(nrm);
-            int w = vote_first<F2>(sqr(sc) == nrm);
+            int w = vote_first<F2>(fp_is_square(nrm));       // a is a square in Fp2 iff its norm is one in Fp
             if (w < 0) continue;
             x.c0 = bcast_fp<F2>(xc.c0, w); x.c1 = bcast_fp<F2>(xc.c1, w);
             a.c0 = bcast_fp<F2>(ac.c0, w); a.c1 = bcast_fp<F2>(ac.c1, w);
-            s = bcast_fp<F2>(sc, w);
+            s = fp_pow<ExpPp1d4>(bcast_fp<F2>(nrm, w));       // sqrt(norm), after the loop has converged
             greatest = bcast_flag<F2>(gr, w);
             break;
         }
@@ -498,6 +505,99 @@ TCB_HD void task_g1_decode(size_t i, const u8 *pts_g1, Jac1Store *out) {
     out[i].x = p.x; out[i].y = p.y; out[i].z = p.z;
 }
 
+// ----------------------------------------------------------------------------- §8(f) row 1: batched point (de)compression
+// Encodings of SURVEY App. B (EXTERNAL pairing 0.16 EncodedPoint): checked decoding = flag bits,
+// x < p, on the curve, AND in the r-order subgroup (PublicKey::from_bytes src/lib.rs:140-146,
+// Signature::from_bytes :246-252, serde projective::deserialize src/serde_impl.rs:187-218).
+template <class F2>
+TCB_HD void g2_compress(u8 *out, const Aff<F2> &a) {
+    if (a.inf) {
+        if (is_writer<F2>()) { for (int i = 0; i < 96; i++) out[i] = 0; out[0] = 0xc0; }
+        return;
+    }
+    bool greatest = fp2_cmp(a.y, -a.y) > 0;
+    store_f2_be<F2>(out, a.x);
+    // flag bits live in the first byte, which belongs to the c1 half (role 1 in a sliced engine)
+    if (!F2::SLICED || my_role<F2>() == 1) out[0] |= greatest ? 0xa0 : 0x80;
+}
+TCB_HD void task_g1_compress(size_t i, const u8 *unc, u8 *out48) {
+    bool ok = true;
+    g1_compress(out48 + 48 * i, load_g1(unc + 96 * i, ok));
+}
+template <class F2>
+TCB_HD void task_g2_compress(size_t i, const u8 *unc, u8 *out96) {
+    bool ok = true;
+    g2_compress<F2>(out96 + 96 * i, load_g2<F2>(unc + 192 * i, ok));
+}
+// status: 0 ok, 3 invalid.  Output: uncompressed affine (all-zero with the infinity flag if invalid).
+TCB_HD void task_g1_decompress(size_t i, const u8 *in48, u8 *out96, u8 *status) {
+    const u8 *in = in48 + 48 * i;
+    u8 *out = out96 + 96 * i;
+    Aff<Fp> a;
+    a.inf = true; a.x = Fp::zero(); a.y = Fp::zero();
+    bool ok = (in[0] & 0x80) != 0;
+    if (ok && (in[0] & 0x40)) {          // infinity: every other bit must be clear
+        ok = in[0] == 0xc0;
+        for (int k = 1; k < 48; k++) ok = ok && in[k] == 0;
+    } else if (ok) {
+        u8 tmp[48];
+        for (int k = 0; k < 48; k++) tmp[k] = in[k];
+        tmp[0] &= 0x1f;
+        Fp x = load_fp_be(tmp, ok);
+        if (ok) {
+            Fp rhs = sqr(x) * x + CONSTS().b1;
+            Fp y = fp_pow<ExpPp1d4>(rhs);
+            ok = sqr(y) == rhs;
+            if (ok) {
+                bool want_greatest = (in[0] & 0x20) != 0;
+                Fp ny = -y;
+                if ((fp_cmp(y, ny) > 0) != want_greatest) y = ny;
+                a.x = x; a.y = y; a.inf = false;
+                ok = jac_is_inf(jac_mul_const<Fp, ExpR>(a));       // subgroup check: r * P == O
+            }
+        }
+    }
+    if (!ok) { a.inf = true; }
+    store_g1(out, a);
+    if (!ok) out[0] = 0;                 // invalid: all-zero output
+    status[i] = ok ? 0 : 3;
+}
+template <class F2>
+TCB_HD void task_g2_decompress(size_t i, const u8 *in96, u8 *out192, u8 *status) {
+    const u8 *in = in96 + 96 * i;
+    u8 *out = out192 + 192 * i;
+    Aff<F2> a;
+    a.inf = true; a.x = F2::zero(); a.y = F2::zero();
+    bool ok = (in[0] & 0x80) != 0;
+    if (ok && (in[0] & 0x40)) {
+        ok = in[0] == 0xc0;
+        for (int k = 1; k < 96; k++) ok = ok && in[k] == 0;
+    } else if (ok) {
+        u8 tmp[96];
+        for (int k = 0; k < 96; k++) tmp[k] = in[k];
+        tmp[0] &= 0x1f;
+        bool dec = true;
+        F2 x = load_f2_be<F2>(tmp, dec);
+        ok = unit_and<F2>(dec);          // a sliced engine validates its own half only
+        if (ok) {
+            const Consts &C = CONSTS();
+            F2 rhs = sqr(x) * x + F2::from_halves(C.b1, C.b1);
+            F2 y;
+            ok = fp2_sqrt(y, rhs);
+            if (ok) {
+                bool want_greatest = (in[0] & 0x20) != 0;
+                F2 ny = -y;
+                if ((fp2_cmp(y, ny) > 0) != want_greatest) y = ny;
+                a.x = x; a.y = y; a.inf = false;
+                ok = jac_is_inf(jac_mul_const<F2, ExpR>(a));
+            }
+        }
+    }
+    if (!ok) a.inf = true;
+    store_g2<F2>(out, a);
+    if (is_writer<F2>()) { if (!ok) out[0] = 0; status[i] = ok ? 0 : 3; }
+}
+
 // ----------------------------------------------------------------------------- constants builder (host side; runs at tcb_init)
 // Computes every derived constant from p, r and the generator coordinates using the same
 // field code, so nothing but the curve definition is hard-coded.
@@ -523,7 +623,8 @@ inline void build_consts(Consts &C) {
     C.r2 = pow2_mod<FpParams>(768);
     C.fr_r1 = pow2_mod<FrParams>(256);
     C.fr_r2 = pow2_mod<FrParams>(512);
-    h_consts.r1 = C.r1; h_consts.r2 = C.r2; h_consts.fr_r1 = C.fr_r1; h_consts.fr_r2 = C.fr_r2;
+    C.r3 = C.r2 * C.r2;   // R^2 * R^2 * R^-1
+    h_consts.r1 = C.r1; h_consts.r2 = C.r2; h_consts.r3 = C.r3; h_consts.fr_r1 = C.fr_r1; h_consts.fr_r2 = C.fr_r2;
     Fp four = Fp::zero();
     four.l[0] = 4;
     C.b1 = fp_to_mont(four);

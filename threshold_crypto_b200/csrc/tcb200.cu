@@ -461,6 +461,29 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *ctx, size_t deg, const u8 *coe
     return sync_all(ctx);
 }
 
+// ---- batched point (de)compression
+static int codec_common(tcb_ctx *ctx, size_t n, const u8 *in, size_t in_w, u8 *out, size_t out_w, u8 *status, int which) {
+    HOST_PROLOGUE
+    FOR_EACH_DEV
+        u8 *din = up(ctx, d, in + in_w * s.lo, in_w * cnt);
+        u8 *dout = (u8 *)arena_alloc(ctx, d, out_w * cnt), *dst = (u8 *)arena_alloc(ctx, d, cnt);
+        if (!din || !dout || !dst) return -1;
+        switch (which) {
+            case 0: RUN(run_g1_compress(st, cnt, din, dout)); break;
+            case 1: RUN(run_g2_compress(st, cnt, din, dout)); break;
+            case 2: RUN(run_g1_decompress(st, cnt, din, dout, dst)); break;
+            default: RUN(run_g2_decompress(st, cnt, din, dout, dst)); break;
+        }
+        if (down(ctx, d, out + out_w * s.lo, dout, out_w * cnt)) return -1;
+        if (status && down(ctx, d, status + s.lo, dst, cnt)) return -1;
+    END_FOR_EACH_DEV
+    return sync_all(ctx);
+}
+extern "C" int tcb_g1_compress_batch(tcb_ctx *ctx, size_t n, const u8 *unc, u8 *out48) { return codec_common(ctx, n, unc, 96, out48, 48, nullptr, 0); }
+extern "C" int tcb_g2_compress_batch(tcb_ctx *ctx, size_t n, const u8 *unc, u8 *out96) { return codec_common(ctx, n, unc, 192, out96, 96, nullptr, 1); }
+extern "C" int tcb_g1_decompress_batch(tcb_ctx *ctx, size_t n, const u8 *in48, u8 *out96, u8 *status) { return codec_common(ctx, n, in48, 48, out96, 96, status, 2); }
+extern "C" int tcb_g2_decompress_batch(tcb_ctx *ctx, size_t n, const u8 *in96, u8 *out192, u8 *status) { return codec_common(ctx, n, in96, 96, out192, 192, status, 3); }
+
 // ----------------------------------------------------------------------------- self-test / probes
 extern "C" int tcb_selftest_fp(tcb_ctx *ctx, size_t n, uint64_t seed) {
     if (!ctx) return -2;
