@@ -87,6 +87,12 @@ int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const uint8_t *coeff_g1, si
 /* SecretKey::public_key / Poly::commitment (src/lib.rs:367-369, src/poly.rs:372-377): g1 * c */
 int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const uint8_t *sk, uint8_t *out_g1);
 
+/* SURVEY §8(f) row 2 — PublicKey::encrypt_with_rng (src/lib.rs:128-137) with the random scalars r
+ * drawn by the caller (Fr::random stays in the Rust shim): u = g1*r, v = xor_with_hash(pk*r, msg),
+ * w = hash_g1_g2(u, v)*r.  v_out has the layout of msgs (same offsets). */
+int tcb_encrypt_batch(tcb_ctx *, size_t n, const uint8_t *pk_g1, const uint8_t *r_fr, const uint8_t *msgs,
+                      const uint64_t *off, uint8_t *u_out_g1, uint8_t *v_out, uint8_t *w_out_g2);
+
 /* SURVEY §8(f) row 1 — batched wire-format codecs.  Compressed encodings of SURVEY App. B (48 B / 96 B);
  * decompression is the CHECKED decode of PublicKey::from_bytes / Signature::from_bytes
  * (src/lib.rs:140-146,246-252) and serde `projective::deserialize` (src/serde_impl.rs:187-218):

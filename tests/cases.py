@@ -92,6 +92,14 @@ def check_all(E, O, n_sig=6, n_comb=3, t=3, deg=6, n_eval=5, seed=7):
     dec, st = E.decrypt_batch(n_comb, t, x1, s1, vs)
     odec, ost = O.decrypt_batch(n_comb, t, x1, s1, vs)
     assert dec == odec and np.array_equal(st, ost)
+    # encrypt: one oracle call per item
+    r = rand_fr(np.random.default_rng(seed + 9), n_comb)
+    plains = [bytes((7 * i + k) & 0xff for k in range(3 + 30 * i)) for i in range(n_comb)]
+    pks = O.g1_mul_gen_batch(rand_fr(np.random.default_rng(seed + 10), n_comb))
+    u, v, w = E.encrypt_batch(pks, r, plains)
+    for i in range(n_comb):
+        ou, ov, ow = O.encrypt(pks[i], r[32 * i:32 * i + 32], plains[i])
+        assert np.array_equal(u[i], ou) and v[i] == ov and np.array_equal(w[i], ow)
     # decrypt shares
     rng = np.random.default_rng(seed + 3)
     ski = rand_fr(rng, n_comb)

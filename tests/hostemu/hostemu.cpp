@@ -97,6 +97,13 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff,
     return 0;
 }
 
+extern "C" int tcb_encrypt_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out, u8 *w_out) {
+    std::vector<u8> h(192 * n);
+    for (size_t i = 0; i < n; i++) task_encrypt_uv(i, pk, r, msgs, off, u_out, v_out);
+    for (size_t i = 0; i < n; i++) task_hash_g1_g2<Fp2>(i, u_out, v_out, off, h.data());
+    for (size_t i = 0; i < n; i++) task_sign<Fp2>(i, r, nullptr, nullptr, h.data(), w_out);
+    return 0;
+}
 extern "C" int tcb_g1_compress_batch(tcb_ctx *, size_t n, const u8 *unc, u8 *out) { for (size_t i = 0; i < n; i++) task_g1_compress(i, unc, out); return 0; }
 extern "C" int tcb_g2_compress_batch(tcb_ctx *, size_t n, const u8 *unc, u8 *out) { for (size_t i = 0; i < n; i++) task_g2_compress<Fp2>(i, unc, out); return 0; }
 extern "C" int tcb_g1_decompress_batch(tcb_ctx *, size_t n, const u8 *in, u8 *out, u8 *st) { for (size_t i = 0; i < n; i++) task_g1_decompress(i, in, out, st); return 0; }

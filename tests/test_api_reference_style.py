@@ -88,3 +88,16 @@ def test_poly_kat(tc):                        # src/poly.rs:783-797: 5 X^3 + X -
     poly = tc.Poly([-2, 1, 0, 5])
     for x, y in ((-1, -8), (2, 40), (3, 136), (5, 628)):
         assert poly.evaluate(x) == y % tc.R
+
+
+def test_simple_enc(tc):                       # src/lib.rs:876-897
+    r = rng()
+    sk_bob, sk_eve = tc.SecretKey(int.from_bytes(r.bytes(40), "little")), tc.SecretKey(int.from_bytes(r.bytes(40), "little"))
+    pk_bob = sk_bob.public_key()
+    msg = b"Muffins in the canteen today! Don't tell Eve!"
+    ct = pk_bob.encrypt_with_rng(r, msg)
+    assert ct.verify()
+    assert sk_bob.decrypt(ct) == msg
+    assert sk_eve.decrypt(ct) != msg                      # Eve gets garbage
+    fake = tc.Ciphertext(ct.u, b"fake news" + ct.v[9:], ct.w)
+    assert not fake.verify() and sk_bob.decrypt(fake) is None

@@ -173,6 +173,14 @@ class Engine:
         self._ck(self.lib.tcb_g1_mul_gen_batch(self.ctx, C.c_size_t(n), _p(sk), _p(out)))
         return out
 
+    def encrypt_batch(self, pk_g1, r_fr, msgs):
+        pk, r = _u8(pk_g1), _u8(r_fr)
+        buf, off = pack_msgs(msgs)
+        n = len(msgs)
+        u = np.zeros((n, 96), np.uint8); v = np.zeros(buf.size, np.uint8); w = np.zeros((n, 192), np.uint8)
+        self._ck(self.lib.tcb_encrypt_batch(self.ctx, C.c_size_t(n), _p(pk), _p(r), _p(buf), _p(off), _p(u), _p(v), _p(w)))
+        return u, [bytes(v[int(off[i]):int(off[i + 1])]) for i in range(n)], w
+
     # ---- wire-format codecs
     def _codec(self, name, data, in_w, out_w, with_status):
         a = _u8(data)

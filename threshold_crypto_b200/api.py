@@ -98,6 +98,11 @@ class PublicKey(_Point):           # PublicKey(G1), src/lib.rs:79
     def verify(self, sig, msg):                        # src/lib.rs:115-117
         return bool(engine().verify_batch(self.raw, sig.raw, [bytes(msg)])[0])
 
+    def encrypt_with_rng(self, rng, msg):              # src/lib.rs:128-137; Fr::random stays on the host
+        r = int.from_bytes(rng.bytes(40), "little") % R
+        u, v, w = engine().encrypt_batch(self.raw, _fr(r), [bytes(msg)])
+        return Ciphertext(u[0], v[0], w[0])
+
 
 class PublicKeyShare(PublicKey):   # src/lib.rs:160
 
@@ -128,6 +133,13 @@ class SecretKey:                   # SecretKey(Fr), src/lib.rs:302
 
     def sign(self, msg):                               # src/lib.rs:379-381
         return Signature(engine().sign_batch(_fr(self.fr), [bytes(msg)])[0])
+
+    def decrypt(self, ct):                             # src/lib.rs:384-391: None if the ciphertext is invalid
+        if not ct.verify():
+            return None
+        g = engine().decrypt_share_batch(_fr(self.fr), ct.u)
+        out, _ = engine().decrypt_batch(1, 0, _fr(1), g, [ct.v])     # t = 0: xor_with_hash(g, v)
+        return out[0]
 
     def __eq__(self, o):
         return isinstance(o, SecretKey) and self.fr == o.fr

@@ -59,23 +59,24 @@ static __device__ Fp rand_fp(u64 &s, int mode) {
         if (limbs_lt_mod<FpParams>(r.l)) return r;
     }
 }
-// 8 independent IMAD.WIDE accumulators per thread, no carries: the integer-MAC ceiling
+// 16 independent IMAD.WIDE.U32 accumulators per thread and nothing else in the loop body: the
+// integer-MAC ceiling (32 MAC/clk/SM on B200; the first version of this probe had 8 accumulators
+// plus a dependent add per row and under-read the ceiling by ~5%, see profiles/r1g_microbench.txt)
 __global__ void __launch_bounds__(256) k_probe_imad(u64 *out, int iters, u32 seed) {
     u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-    u64 acc[8];
+    u64 acc[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k;
+    for (int k = 0; k < 16; k++) acc[k] = k;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < 4; r++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = (u64)a * (u32)(b + k) + acc[k];
-            a += (u32)acc[0];
+            for (int k = 0; k < 16; k++) acc[k] = (u64)(a + k) * (u32)(b + r) + acc[k];
         }
     }
     u64 s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
+    for (int k = 0; k < 16; k++) s ^= acc[k];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 // 2 independent Montgomery-multiply chains per thread
@@ -87,6 +88,10 @@ __global__ void __launch_bounds__(256) k_probe_fpmul(Fp *out, int iters, u64 see
 }
 
 
+__global__ void __launch_bounds__(128) k_encrypt_uv(size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_encrypt_uv(i, pk, r, msgs, off, u_out, v_out);
+}
 __global__ void __launch_bounds__(128) k_g1_compress(size_t n, const u8 *unc, u8 *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) task_g1_compress(i, unc, out);
@@ -120,6 +125,9 @@ void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab) {
 }
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out) {
     if (n) k_commit_eval<<<grid1(n), 128, 0, st>>>(n, deg, (const Jac1Store *)tab, x, out);
+}
+void run_encrypt_uv(cudaStream_t st, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out) {
+    if (n) k_encrypt_uv<<<grid1(n), 128, 0, st>>>(n, pk, r, msgs, off, u_out, v_out);
 }
 void run_g1_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out) { if (n) k_g1_compress<<<grid1(n), 128, 0, st>>>(n, unc, out); }
 void run_g1_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status) { if (n) k_g1_decompress<<<grid1(n), 128, 0, st>>>(n, in, out, status); }

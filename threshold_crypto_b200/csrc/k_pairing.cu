@@ -9,10 +9,11 @@ using namespace tcb;
 #endif
 __global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_verify_g2_quad(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    if (i >= n) return;
+    bool live = i < n;
+    if (!live) i = n - 1;          // tail lanes recompute the last item: no early exit (block-wide phase barriers)
     bool enc_ok;
     bool res = pairing_eq_quad(a + 96 * i, b + 192 * i, c ? c + 96 * i : nullptr, d + 192 * i, enc_ok);
-    if ((threadIdx.x & 3) == 0) ok[i] = (res && enc_ok) ? 1 : 0;
+    if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok) ? 1 : 0;
 }
 // ---- self-test and roofline probes
 static __device__ __forceinline__ u64 splitmix(u64 &s) {

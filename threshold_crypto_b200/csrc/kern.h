@@ -37,6 +37,7 @@ void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out)
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);
+void run_encrypt_uv(cudaStream_t st, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out);
 void run_g1_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out);
 void run_g1_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status);
 void run_probe_imad(cudaStream_t st, int blocks, int threads, u64 *out, int iters);

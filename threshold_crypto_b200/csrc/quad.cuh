@@ -20,6 +20,17 @@ namespace tcb {
 
 typedef Fp6T<Fp2S> Fp6S;
 
+// Phase lock: the hot loop is a ~450 KB straight-line instruction stream per Miller iteration, far
+// beyond the instruction caches, and every warp fetches it from L2 on its own.  The four warps of
+// a block sit on the four SMSPs of the SM (no pipe contention between them), so re-aligning them at
+// block-uniform points lets them share instruction-cache fills.  All threads of the block must
+// reach every TCB_PHASE() (no early exit, no call under a non-uniform condition).
+#if defined(TCB_PHASE_SYNC)
+#define TCB_PHASE() __syncthreads()
+#else
+#define TCB_PHASE() ((void)0)
+#endif
+
 TCB_D u32 quad_pair() { return (threadIdx.x >> 1) & 1u; }
 TCB_D u32 quad_mask() { return 0xFu << (threadIdx.x & 28u); }
 TCB_D Fp xq(const Fp &a) {   // exchange with the same role in the other pair of the quad
@@ -164,17 +175,20 @@ __device__ __noinline__ Fp12Q fp12_exp_by_x(const Fp12Q &f, u64 x) {
     int top = 63;
     while (!((x >> top) & 1)) top--;
     for (int i = top - 1; i >= 0; i--) {
+        TCB_PHASE();
         acc = fp12_cyclo_sqr(acc);
-        if ((x >> i) & 1) acc = fp12_mul(acc, f);
+        if ((x >> i) & 1) { TCB_PHASE(); acc = fp12_mul(acc, f); }
     }
     return fp12_conj(acc);
 }
 // same chain as final_exponentiation<F2> in tower.cuh
 __device__ __noinline__ Fp12Q final_exponentiation(const Fp12Q &in) {
     Fp12Q f2 = fp12_inv(in);
+    TCB_PHASE();
     Fp12Q r = fp12_mul(fp12_conj(in), f2);
     f2 = r;
     r = fp12_mul(fp12_frob(r, 2), f2);
+    TCB_PHASE();
     const u64 x = TCB_BLS_X;
     Fp12Q y0 = fp12_cyclo_sqr(r);
     Fp12Q y1 = fp12_exp_by_x(y0, x);
@@ -234,17 +248,24 @@ __device__ __noinline__ bool pairing_eq_quad(const u8 *a_g1, const u8 *b_g2, con
     Fp12Q f = q12_one();
     const u64 xs = TCB_BLS_X >> 1;
     for (int i = 61; i >= 0; i--) {
+        TCB_PHASE();
         LineS l = scale_line(doubling_step(t), p);
+        TCB_PHASE();
         apply_lines(f, l, act, act_o);
         if ((xs >> i) & 1) {
+            TCB_PHASE();
             l = scale_line(addition_step(t, q), p);
+            TCB_PHASE();
             apply_lines(f, l, act, act_o);
         }
+        TCB_PHASE();
         f = fp12_sqr(f);
     }
+    TCB_PHASE();
     LineS l = scale_line(doubling_step(t), p);
     apply_lines(f, l, act, act_o);
     f = fp12_conj(f);
+    TCB_PHASE();
     return fp12_is_one(final_exponentiation(f));
 }
 

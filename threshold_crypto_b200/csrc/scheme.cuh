@@ -499,6 +499,20 @@ TCB_HD void task_commit_eval(size_t i, size_t deg, const Jac1Store *coeff, const
     }
     store_g1(out_g1 + 96 * i, jac_to_aff(acc));
 }
+// §8(f) row 2, PublicKey::encrypt_with_rng (src/lib.rs:128-137) with the random scalar r supplied by
+// the caller: u = g1 * r, v = xor_with_hash(pk * r, msg).  (w = hash_g1_g2(u, v) * r is produced by
+// k_hash_g1_g2 + k_sign afterwards.)
+TCB_HD void task_encrypt_uv(size_t i, const u8 *pk_g1, const u8 *r_fr, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out) {
+    u32 k[8];
+    load_scalar_le(k, r_fr + 32 * i);
+    bool ok = true;
+    Aff<Fp> g;
+    g.x = CONSTS().g1x; g.y = CONSTS().g1y; g.inf = false;
+    store_g1(u_out + 96 * i, jac_to_aff(jac_mul_glv2(g, k)));
+    Aff<Fp> pk = load_g1(pk_g1 + 96 * i, ok);
+    Aff<Fp> s = jac_to_aff(jac_mul_glv2(pk, k));
+    xor_with_hash(v_out + off[i], s, msgs + off[i], (size_t)(off[i + 1] - off[i]));
+}
 TCB_HD void task_g1_decode(size_t i, const u8 *pts_g1, Jac1Store *out) {
     bool ok = true;
     Jac<Fp> p = jac_from_aff(load_g1(pts_g1 + 96 * i, ok));

@@ -461,6 +461,30 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *ctx, size_t deg, const u8 *coe
     return sync_all(ctx);
 }
 
+// ---- PublicKey::encrypt_with_rng with caller-supplied r (src/lib.rs:128-137)
+extern "C" int tcb_encrypt_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off,
+                                 u8 *u_out, u8 *v_out, u8 *w_out) {
+    HOST_PROLOGUE
+    std::vector<std::vector<u64>> keep;
+    keep.reserve(G);
+    FOR_EACH_DEV
+        u8 *dm; u64 *doff;
+        if (up_msgs(ctx, d, msgs, off, s.lo, s.hi, keep, dm, doff)) return -1;
+        size_t mbytes = (size_t)(off[s.hi] - off[s.lo]);
+        u8 *dpk = up(ctx, d, pk + 96 * s.lo, 96 * cnt), *dr = up(ctx, d, r + 32 * s.lo, 32 * cnt);
+        u8 *du = (u8 *)arena_alloc(ctx, d, 96 * cnt), *dv = (u8 *)arena_alloc(ctx, d, mbytes);
+        u8 *dh = (u8 *)arena_alloc(ctx, d, 192 * cnt), *dw = (u8 *)arena_alloc(ctx, d, 192 * cnt);
+        if (!dpk || !dr || !du || !dv || !dh || !dw) return -1;
+        RUN(run_encrypt_uv(st, cnt, dpk, dr, dm, doff, du, dv));
+        RUN(run_hash_g1_g2(st, cnt, du, dv, doff, dh));
+        RUN(run_sign(st, cnt, dr, nullptr, nullptr, dh, dw));
+        if (down(ctx, d, u_out + 96 * s.lo, du, 96 * cnt) || down(ctx, d, v_out + off[s.lo], dv, mbytes) ||
+            down(ctx, d, w_out + 192 * s.lo, dw, 192 * cnt)) return -1;
+        CK(cudaMemsetAsync(dr, 0, 32 * cnt, st));     // the encryption randomness is secret
+    END_FOR_EACH_DEV
+    return sync_all(ctx);
+}
+
 // ---- batched point (de)compression
 static int codec_common(tcb_ctx *ctx, size_t n, const u8 *in, size_t in_w, u8 *out, size_t out_w, u8 *status, int which) {
     HOST_PROLOGUE
