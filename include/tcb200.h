@@ -87,6 +87,12 @@ int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const uint8_t *coeff_g1, si
 /* SecretKey::public_key / Poly::commitment (src/lib.rs:367-369, src/poly.rs:372-377): g1 * c */
 int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const uint8_t *sk, uint8_t *out_g1);
 
+/* SURVEY §8(f) row 3 — linear combinations out_i = sum_{k<m} s_{i,k} P_{i,k} (canonical Fr scalars, points of
+ * order r).  BivarCommitment::row / evaluate (src/poly.rs:693-726) call it with the power products
+ * x^j (resp. x^i y^j) as scalars; Commitment addition / Poly::commitment of sums reduce to it as well. */
+int tcb_g1_lincomb_batch(tcb_ctx *, size_t n, size_t m, const uint8_t *scalars_fr, const uint8_t *pts_g1, uint8_t *out_g1);
+int tcb_g2_lincomb_batch(tcb_ctx *, size_t n, size_t m, const uint8_t *scalars_fr, const uint8_t *pts_g2, uint8_t *out_g2);
+
 /* SURVEY §8(f) row 2 — PublicKey::encrypt_with_rng (src/lib.rs:128-137) with the random scalars r
  * drawn by the caller (Fr::random stays in the Rust shim): u = g1*r, v = xor_with_hash(pk*r, msg),
  * w = hash_g1_g2(u, v)*r.  v_out has the layout of msgs (same offsets). */

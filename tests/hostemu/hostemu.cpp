@@ -97,6 +97,20 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff,
     return 0;
 }
 
+extern "C" int tcb_g1_lincomb_batch(tcb_ctx *, size_t n, size_t m, const u8 *sc, const u8 *pts, u8 *out) {
+    std::vector<Jac1Store> terms(n * m);
+    std::vector<u8> st(n);
+    for (size_t u = 0; u < n * m; u++) task_g1_mul_store(u, (const u32 *)sc, pts, terms.data(), st.data(), m);
+    for (size_t i = 0; i < n; i++) store_g1(out + 96 * i, g1_sum(i, m, terms.data()));
+    return 0;
+}
+extern "C" int tcb_g2_lincomb_batch(tcb_ctx *, size_t n, size_t m, const u8 *sc, const u8 *pts, u8 *out) {
+    std::vector<JacStore<Fp2>> terms(n * m);
+    std::vector<u8> st(n);
+    for (size_t u = 0; u < n * m; u++) task_g2_mul_store<Fp2>(u, (const u32 *)sc, pts, terms.data(), st.data(), m);
+    for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, m, terms.data(), out);
+    return 0;
+}
 extern "C" int tcb_encrypt_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out, u8 *w_out) {
     std::vector<u8> h(192 * n);
     for (size_t i = 0; i < n; i++) task_encrypt_uv(i, pk, r, msgs, off, u_out, v_out);

@@ -101,3 +101,41 @@ def test_simple_enc(tc):                       # src/lib.rs:876-897
     assert sk_eve.decrypt(ct) != msg                      # Eve gets garbage
     fake = tc.Ciphertext(ct.u, b"fake news" + ct.v[9:], ct.w)
     assert not fake.verify() and sk_bob.decrypt(fake) is None
+
+
+def test_distributed_key_generation(tc):       # src/poly.rs:819-900 (dealers 3, nodes 5, faulty 2)
+    r = rng()
+    dealer_num, node_num, faulty_num = 3, 5, 2
+    sec_keys = [0] * node_num
+    pub_bivar_polys = []
+    for _ in range(dealer_num):
+        bi_poly = tc.BivarPoly.random(faulty_num, r)
+        bi_commit = bi_poly.commitment()
+        pub_bivar_polys.append(bi_commit)
+        for m in range(1, node_num + 1):
+            row_poly = bi_poly.row(m)
+            row_commit = bi_commit.row(m)
+            assert row_poly.commitment() == row_commit                      # the row matches the public commitment
+            for s in range(1, node_num + 1):
+                val = row_poly.evaluate(s)
+                assert np.array_equal(bi_commit.evaluate(m, s), tc.engine().g1_mul_gen_batch(tc._fr(val))[0])
+                assert bi_poly.evaluate(m, s) == val
+            # f(m, 0) from faulty_num + 1 column values by interpolation (src/poly.rs:868-877)
+            received = [(s, bi_poly.evaluate(m, s)) for s in range(1, faulty_num + 2)]
+            sec_keys[m - 1] = (sec_keys[m - 1] + tc.Poly.interpolate(received).evaluate(0)) % tc.R
+    # the summed commitment's row(0) is the master commitment; its evaluations are the key shares' public keys
+    sum_commit = pub_bivar_polys[0].row(0)
+    for bc in pub_bivar_polys[1:]:
+        sum_commit = sum_commit + bc.row(0)
+    for m in range(1, node_num + 1):
+        assert np.array_equal(sum_commit.evaluate(m), tc.engine().g1_mul_gen_batch(tc._fr(sec_keys[m - 1]))[0])
+
+
+def test_poly_algebra(tc):                    # src/poly.rs:783-797 incl. interpolation
+    x3, x1 = tc.Poly.monomial(3), tc.Poly.monomial(1)
+    poly = x3 * 5 + x1 - 2
+    assert poly == tc.Poly([-2, 1, 0, 5])
+    samples = [(-1, -8), (2, 40), (3, 136), (5, 628)]
+    for x, y in samples:
+        assert poly.evaluate(x) == y % tc.R
+    assert tc.Poly.interpolate(samples) == poly

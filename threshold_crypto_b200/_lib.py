@@ -173,6 +173,20 @@ class Engine:
         self._ck(self.lib.tcb_g1_mul_gen_batch(self.ctx, C.c_size_t(n), _p(sk), _p(out)))
         return out
 
+    def g1_lincomb_batch(self, n, m, scalars, pts):
+        sc, p = _u8(scalars), _u8(pts)
+        assert sc.size == n * m * 32 and p.size == n * m * 96
+        out = np.zeros((n, 96), np.uint8)
+        self._ck(self.lib.tcb_g1_lincomb_batch(self.ctx, C.c_size_t(n), C.c_size_t(m), _p(sc), _p(p), _p(out)))
+        return out
+
+    def g2_lincomb_batch(self, n, m, scalars, pts):
+        sc, p = _u8(scalars), _u8(pts)
+        assert sc.size == n * m * 32 and p.size == n * m * 192
+        out = np.zeros((n, 192), np.uint8)
+        self._ck(self.lib.tcb_g2_lincomb_batch(self.ctx, C.c_size_t(n), C.c_size_t(m), _p(sc), _p(p), _p(out)))
+        return out
+
     def encrypt_batch(self, pk_g1, r_fr, msgs):
         pk, r = _u8(pk_g1), _u8(r_fr)
         buf, off = pack_msgs(msgs)

@@ -182,6 +182,54 @@ class Poly:                        # poly::Poly, src/poly.rs:40-44 (Fr algebra s
     def commitment(self):                              # src/poly.rs:372-377: g1 * c_k on the GPU
         return Commitment(engine().g1_mul_gen_batch(_frs(self.coeff)))
 
+    # Fr-side algebra (src/poly.rs:63-194): cheap 255-bit work, stays on the host
+    def __add__(self, o):
+        o = o if isinstance(o, Poly) else Poly([o])
+        n = max(len(self.coeff), len(o.coeff))
+        return Poly([(a + b) % R for a, b in zip(self.coeff + [0] * (n - len(self.coeff)), o.coeff + [0] * (n - len(o.coeff)))])._trim()
+
+    def __sub__(self, o):
+        o = o if isinstance(o, Poly) else Poly([o])
+        return self + Poly([(-c) % R for c in o.coeff])
+
+    def __mul__(self, o):
+        if not isinstance(o, Poly):
+            return Poly([c * int(o) % R for c in self.coeff])._trim()
+        if not self.coeff or not o.coeff:
+            return Poly([])
+        out = [0] * (len(self.coeff) + len(o.coeff) - 1)
+        for i, a in enumerate(self.coeff):
+            for j, b in enumerate(o.coeff):
+                out[i + j] = (out[i + j] + a * b) % R
+        return Poly(out)._trim()
+
+    def _trim(self):                                   # remove_zeros, src/poly.rs:380-384
+        while self.coeff and self.coeff[-1] == 0:
+            self.coeff.pop()
+        return self
+
+    def __eq__(self, o):
+        return isinstance(o, Poly) and self.coeff == o.coeff
+
+    @staticmethod
+    def monomial(degree):
+        return Poly([0] * degree + [1])
+
+    @staticmethod
+    def interpolate(samples):                          # src/poly.rs:388-417 (Lagrange through distinct points)
+        pts = [(into_fr(x), into_fr(y)) for x, y in samples]
+        if len({x for x, _ in pts}) != len(pts):
+            raise ValueError("interpolate: sample points must be distinct")     # the reference panics (poly.rs:407)
+        res = Poly([])
+        for i, (xi, yi) in enumerate(pts):
+            num, den = Poly([1]), 1
+            for j, (xj, _) in enumerate(pts):
+                if j != i:
+                    num = num * Poly([(-xj) % R, 1])
+                    den = den * (xi - xj) % R
+            res = res + num * (yi * pow(den, R - 2, R) % R)
+        return res
+
 
 class Commitment:                  # poly::Commitment, src/poly.rs:429-433
     def __init__(self, coeff_g1):
@@ -195,6 +243,73 @@ class Commitment:                  # poly::Commitment, src/poly.rs:429-433
 
     def evaluate_batch(self, idx):
         return engine().commitment_eval_batch(self.coeff, _frs([into_fr(i) for i in idx]))
+
+    def __add__(self, o):            # src/poly.rs:436-470: coefficient-wise G1 addition
+        n = max(self.coeff.shape[0], o.coeff.shape[0])
+        inf = np.zeros(96, np.uint8); inf[0] = 0x40
+        a = np.concatenate([self.coeff, np.tile(inf, (n - self.coeff.shape[0], 1))]) if self.coeff.shape[0] < n else self.coeff
+        b = np.concatenate([o.coeff, np.tile(inf, (n - o.coeff.shape[0], 1))]) if o.coeff.shape[0] < n else o.coeff
+        pts = np.stack([a, b], axis=1).reshape(-1, 96)
+        return Commitment(engine().g1_lincomb_batch(n, 2, _frs([1] * (2 * n)), pts))
+
+    def __eq__(self, o):
+        return isinstance(o, Commitment) and np.array_equal(self.coeff, o.coeff)
+
+
+def coeff_pos(i, j):                # src/poly.rs:744-748
+    i, j = (i, j) if j >= i else (j, i)
+    return i + j * (j + 1) // 2
+
+
+def _powers(x, degree):             # src/poly.rs:729-738
+    x = into_fr(x)
+    out, cur = [], 1
+    for _ in range(degree + 1):
+        out.append(cur)
+        cur = cur * x % R
+    return out
+
+
+class BivarPoly:                    # poly::BivarPoly, src/poly.rs:513-650 (symmetric, Fr only: host side)
+    def __init__(self, degree, coeff):
+        self.degree, self.coeff = degree, [int(c) % R for c in coeff]
+        assert len(self.coeff) == coeff_pos(degree, degree) + 1
+
+    @staticmethod
+    def random(degree, rng):
+        return BivarPoly(degree, [int.from_bytes(rng.bytes(40), "little") % R for _ in range(coeff_pos(degree, degree) + 1)])
+
+    def evaluate(self, x, y):
+        xp, yp = _powers(x, self.degree), _powers(y, self.degree)
+        return sum(self.coeff[coeff_pos(i, j)] * xp[i] * yp[j] for i in range(self.degree + 1) for j in range(self.degree + 1)) % R
+
+    def row(self, x):
+        xp = _powers(x, self.degree)
+        return Poly([sum(self.coeff[coeff_pos(i, j)] * xp[j] for j in range(self.degree + 1)) % R for i in range(self.degree + 1)])
+
+    def commitment(self):            # src/poly.rs:627-633: g1 * c on the GPU
+        return BivarCommitment(self.degree, engine().g1_mul_gen_batch(_frs(self.coeff)))
+
+
+class BivarCommitment:              # poly::BivarCommitment, src/poly.rs:652-726 — G1 sweeps on the GPU
+    def __init__(self, degree, coeff_g1):
+        self.degree = degree
+        self.coeff = np.ascontiguousarray(coeff_g1, dtype=np.uint8).reshape(-1, 96)
+        assert self.coeff.shape[0] == coeff_pos(degree, degree) + 1     # serde validation, src/serde_impl.rs:150-161
+
+    def evaluate(self, x, y):        # src/poly.rs:693-709
+        d = self.degree
+        xp, yp = _powers(x, d), _powers(y, d)
+        idx = [coeff_pos(i, j) for i in range(d + 1) for j in range(d + 1)]
+        sc = _frs([xp[i] * yp[j] % R for i in range(d + 1) for j in range(d + 1)])
+        return engine().g1_lincomb_batch(1, (d + 1) ** 2, sc, self.coeff[idx])[0]
+
+    def row(self, x):                # src/poly.rs:712-726
+        d = self.degree
+        xp = _powers(x, d)
+        idx = [coeff_pos(i, j) for i in range(d + 1) for j in range(d + 1)]
+        sc = _frs([xp[j] for i in range(d + 1) for j in range(d + 1)])
+        return Commitment(engine().g1_lincomb_batch(d + 1, d + 1, sc, self.coeff[idx]))
 
 
 class SecretKeySet:                # src/lib.rs:630-688

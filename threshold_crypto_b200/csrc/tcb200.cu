@@ -461,6 +461,27 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *ctx, size_t deg, const u8 *coe
     return sync_all(ctx);
 }
 
+// ---- out_i = sum_k s_{i,k} P_{i,k}  (BivarCommitment::row / evaluate, src/poly.rs:693-726:
+// the caller supplies the Fr power products as scalars).  Same per-term + sum kernels as interpolate.
+static int lincomb_common(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out, int g2) {
+    HOST_PROLOGUE
+    size_t pw = g2 ? 192 : 96;
+    if (m == 0) { if (ctx) ctx->err = "m must be >= 1"; return -2; }
+    FOR_EACH_DEV
+        u8 *dsc = up(ctx, d, scalars + 32 * m * s.lo, 32 * m * cnt), *dp = up(ctx, d, pts + pw * m * s.lo, pw * m * cnt);
+        u8 *dout = (u8 *)arena_alloc(ctx, d, pw * cnt), *dst = (u8 *)arena_alloc(ctx, d, cnt);
+        void *terms = arena_alloc(ctx, d, cnt * m * (g2 ? g2_term_bytes() : g1_term_bytes()));
+        if (!dsc || !dp || !dout || !dst || !terms) return -1;
+        // canonical little-endian scalars are exactly the limb layout the term kernels read
+        if (g2) { RUN(run_g2_mul_store(st, cnt * m, (const u32 *)dsc, dp, terms, dst, m)); RUN(run_g2_sum(st, cnt, m, terms, dout)); }
+        else { RUN(run_g1_mul_store(st, cnt * m, (const u32 *)dsc, dp, terms, dst, m)); RUN(run_g1_sum(st, cnt, m, terms, dout)); }
+        if (down(ctx, d, out + pw * s.lo, dout, pw * cnt)) return -1;
+    END_FOR_EACH_DEV
+    return sync_all(ctx);
+}
+extern "C" int tcb_g1_lincomb_batch(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out) { return lincomb_common(ctx, n, m, scalars, pts, out, 0); }
+extern "C" int tcb_g2_lincomb_batch(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out) { return lincomb_common(ctx, n, m, scalars, pts, out, 1); }
+
 // ---- PublicKey::encrypt_with_rng with caller-supplied r (src/lib.rs:128-137)
 extern "C" int tcb_encrypt_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off,
                                  u8 *u_out, u8 *v_out, u8 *w_out) {
