@@ -46,6 +46,9 @@ int tcb_init(tcb_ctx **ctx, const int *device_ids, int n_devices);
 void tcb_free(tcb_ctx *ctx);
 const char *tcb_last_error(const tcb_ctx *ctx);
 int tcb_set_engine(tcb_ctx *ctx, int engine);
+/* Tuning knob of the multi-scalar multiplication behind combine / decrypt / lincomb: partial sums per
+ * item (shared doublings vs. parallelism).  0 (default) = chosen per call from the batch shape. */
+int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups);
 /* number of kernel launches issued through ctx since tcb_init (bench.py's gpu_launches) */
 uint64_t tcb_launch_count(const tcb_ctx *ctx);
 

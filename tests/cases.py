@@ -164,6 +164,48 @@ def check_edges(E, O):
     assert dec == odec
 
 
+def check_msm(E, O, n=3, m=5, seed=21):
+    """The shared-doubling multi-scalar multiplication behind combine / decrypt / lincomb against
+    sum_i k_i (a_i G) = (sum_i k_i a_i) G computed with the oracle's single scalar multiplications.
+    Shares include: zero / one / r-1 / even / odd scalars, the point at infinity, a repeated
+    (P, k) pair (accumulator == table entry: doubling branch of the mixed addition) and a
+    (P, k), (-P, k) pair (accumulator returns to infinity)."""
+    rng = np.random.default_rng(seed)
+    for group in (1, 2):
+        width = 96 if group == 1 else 192
+        inf = INF1 if group == 1 else INF2
+        gen = (lambda a: O.g1_mul_gen_batch(fr_bytes(a))) if group == 1 else \
+              (lambda a: O.sign_g2_batch(fr_bytes(a), np.tile(O.g2_generator(), (len(a), 1))))
+        a_all, k_all, inf_mask = [], [], []
+        for i in range(n):
+            a = [int.from_bytes(rng.bytes(40), "little") % R for _ in range(m)]
+            k = [int.from_bytes(rng.bytes(40), "little") % R for _ in range(m)]
+            mask = [False] * m
+            if i == 0:
+                k[0], k[1], k[2] = 0, 1, R - 1
+                k[3] &= ~1; k[4] |= 1
+            elif i == 1:
+                a[1], k[1] = a[0], k[0]               # repeated pair
+                a[3], k[3] = (R - a[2]) % R, k[2]     # P and -P with the same scalar
+            else:
+                mask[1] = True                        # infinity share
+                if m > 3:
+                    mask[3] = True
+            a_all += a; k_all += k; inf_mask += mask
+        pts = gen(a_all)
+        for j, isinf in enumerate(inf_mask):
+            if isinf:
+                pts[j] = inf
+        total = [sum(k_all[i * m + s] * a_all[i * m + s] for s in range(m) if not inf_mask[i * m + s]) % R for i in range(n)]
+        expect = gen(total)
+        for i in range(n):
+            if total[i] == 0:
+                expect[i] = inf
+        fn = E.g1_lincomb_batch if group == 1 else E.g2_lincomb_batch
+        out = fn(n, m, fr_bytes(k_all), pts)
+        assert out.shape == (n, width) and np.array_equal(out, expect)
+
+
 def check_codecs(E, O, golden=None, seed=9, n=6):
     """compress / checked decompress against the oracle, incl. infinity and the
     invalid encodings (x >= p, off-curve, wrong flags, on-curve-but-not-in-subgroup)."""

@@ -45,32 +45,50 @@ extern "C" int tcb_sign_g2_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *h,
     for (size_t i = 0; i < n; i++) task_sign<Fp2>(i, sk, nullptr, nullptr, h, out);
     return 0;
 }
+// groups per item used by the emulated multi-scalar multiplication (set by tests to cover G = 1, 2, m)
+static size_t g_groups = 2;
+extern "C" void tcb_emu_set_groups(size_t g) { g_groups = g ? g : 1; }
+extern "C" int tcb_set_msm_groups(tcb_ctx *, size_t g) { g_groups = g ? g : 2; return 0; }
+static void g2_msm(size_t n, size_t m, const u32 *k, const u8 *pts, u8 *out, u8 *status) {
+    size_t G = g_groups < m ? g_groups : m;
+    std::vector<AffStore<Fp2>> tab(n * m * 8);
+    std::vector<Gls4Digits> dg(n * m);
+    std::vector<JacStore<Fp2>> part(n * G);
+    for (size_t u = 0; u < n * m; u++) task_g2_msm_prep<Fp2>(u, k, pts, tab.data(), dg.data(), status, m);
+    for (size_t w = 0; w < n * G; w++) task_g2_msm_acc<Fp2>(w, m, G, tab.data(), dg.data(), part.data());
+    for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, G, part.data(), out);
+}
+static void g1_msm(size_t n, size_t m, const u32 *k, const u8 *pts, Jac1Store *part, size_t G, u8 *status) {
+    std::vector<Aff1Store> tab(n * m * 2);
+    std::vector<Glv2Digits> dg(n * m);
+    for (size_t u = 0; u < n * m; u++) task_g1_msm_prep(u, k, pts, tab.data(), dg.data(), status, m);
+    for (size_t w = 0; w < n * G; w++) task_g1_msm_acc(w, m, G, tab.data(), dg.data(), part);
+}
 extern "C" int tcb_combine_g2_batch(tcb_ctx *, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     memset(status, 0, n);
     if (t == 0) { memcpy(out, shares, n * 192); return 0; }
     size_t m = t + 1;
     std::vector<u32> lam(n * m * 8);
-    std::vector<JacStore<Fp2>> terms(n * m);
     for (size_t i = 0; i < n; i++)
         for (size_t k = 0; k < m; k++) lagrange_coeff(x + i * m * 32, m, k, &lam[8 * (i * m + k)], status[i]);
-    for (size_t u = 0; u < n * m; u++) task_g2_mul_store<Fp2>(u, lam.data(), shares, terms.data(), status, m);
-    for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, m, terms.data(), out);
+    g2_msm(n, m, lam.data(), shares, out, status);
     return 0;
 }
 static int combine_g1(size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status, int mode, const u8 *v, const u64 *voff) {
     memset(status, 0, n);
     size_t m = t + 1;
     std::vector<u32> lam(n * m * 8);
-    std::vector<Jac1Store> terms(n * m);
+    size_t G = g_groups < m ? g_groups : m;
+    std::vector<Jac1Store> terms(n * G);
     if (t > 0) {
         for (size_t i = 0; i < n; i++)
             for (size_t k = 0; k < m; k++) lagrange_coeff(x + i * m * 32, m, k, &lam[8 * (i * m + k)], status[i]);
-        for (size_t u = 0; u < n * m; u++) task_g1_mul_store(u, lam.data(), shares, terms.data(), status, m);
+        g1_msm(n, m, lam.data(), shares, terms.data(), G, status);
     }
     for (size_t i = 0; i < n; i++) {
         Aff<Fp> g;
         bool ok = true;
-        if (t > 0) g = g1_sum(i, m, terms.data()); else g = load_g1(shares + 96 * i, ok);
+        if (t > 0) g = g1_sum(i, G, terms.data()); else g = load_g1(shares + 96 * i, ok);
         if (mode == 0) store_g1(out + 96 * i, g);
         else xor_with_hash(out + voff[i], g, v + voff[i], (size_t)(voff[i + 1] - voff[i]));
     }
@@ -98,17 +116,16 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff,
 }
 
 extern "C" int tcb_g1_lincomb_batch(tcb_ctx *, size_t n, size_t m, const u8 *sc, const u8 *pts, u8 *out) {
-    std::vector<Jac1Store> terms(n * m);
+    size_t G = g_groups < m ? g_groups : m;
+    std::vector<Jac1Store> terms(n * G);
     std::vector<u8> st(n);
-    for (size_t u = 0; u < n * m; u++) task_g1_mul_store(u, (const u32 *)sc, pts, terms.data(), st.data(), m);
-    for (size_t i = 0; i < n; i++) store_g1(out + 96 * i, g1_sum(i, m, terms.data()));
+    g1_msm(n, m, (const u32 *)sc, pts, terms.data(), G, st.data());
+    for (size_t i = 0; i < n; i++) store_g1(out + 96 * i, g1_sum(i, G, terms.data()));
     return 0;
 }
 extern "C" int tcb_g2_lincomb_batch(tcb_ctx *, size_t n, size_t m, const u8 *sc, const u8 *pts, u8 *out) {
-    std::vector<JacStore<Fp2>> terms(n * m);
     std::vector<u8> st(n);
-    for (size_t u = 0; u < n * m; u++) task_g2_mul_store<Fp2>(u, (const u32 *)sc, pts, terms.data(), st.data(), m);
-    for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, m, terms.data(), out);
+    g2_msm(n, m, (const u32 *)sc, pts, out, st.data());
     return 0;
 }
 extern "C" int tcb_encrypt_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out, u8 *w_out) {

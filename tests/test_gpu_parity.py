@@ -132,6 +132,24 @@ def test_full_size_properties_config3_4_5(gpu_engine, O):
     O.set_threads(1)
 
 
+def test_msm_groupings_and_edges(gpu_engine, O):
+    """The shared-doubling multi-scalar multiplication with forced 1 / 2 / 3 / m partial sums per item and
+    with the automatic choice: zero / one / r-1 scalars, infinity shares, repeated and cancelling pairs."""
+    E = gpu_engine
+    try:
+        for g in (1, 2, 3, 1000, 0):
+            E.set_msm_groups(g)
+            cases.check_msm(E, O, n=5, m=7, seed=30 + g % 7)
+            x, s, master = cases.make_combine_batch(O, 6, 4, 50 + g % 7, group=2)
+            out, st = E.combine_g2_batch(6, 4, x, s)
+            assert np.array_equal(out, master) and not st.any()
+            x, s, master = cases.make_combine_batch(O, 6, 4, 60 + g % 7, group=1)
+            out, st = E.combine_g1_batch(6, 4, x, s)
+            assert np.array_equal(out, master) and not st.any()
+    finally:
+        E.set_msm_groups(0)
+
+
 def test_multi_device_ctx_matches_single(O):
     """A ctx over all visible devices shards contiguous slices and returns the same bytes."""
     import torch

@@ -35,6 +35,19 @@ def test_hostemu_golden(emu, golden):
     assert [bytes(p).hex() for p in out] == ce["out"]
 
 
+def test_hostemu_msm_groupings(emu, O):
+    """Shared-doubling MSM with 1, 2 and m groups per item (m groups = one share per unit)."""
+    try:
+        for g in (1, 2, 64):
+            emu.set_msm_groups(g)
+            cases.check_msm(emu, O, n=3, m=5, seed=21 + g)
+            x, s, master = cases.make_combine_batch(O, 2, 3, 40 + g, group=2)
+            out, st = emu.combine_g2_batch(2, 3, x, s)
+            assert np.array_equal(out, master) and not st.any()
+    finally:
+        emu.set_msm_groups(0)
+
+
 def test_binary_gcd_inverse_and_legendre_symbol(emu):
     """fp_inv (branch-free binary GCD) == Fermat inverse, fp_is_square (binary Jacobi) == Euler
     criterion, on random elements and the edge values 0, 1, p-1 (host instantiation of tower.cuh)."""

@@ -82,6 +82,10 @@ class Engine:
     def set_engine(self, engine):
         self._ck(self.lib.tcb_set_engine(self.ctx, int(engine)))
 
+    def set_msm_groups(self, groups):
+        """Partial sums per item of the shared-doubling multi-scalar multiplication (0 = auto)."""
+        self._ck(self.lib.tcb_set_msm_groups(self.ctx, C.c_size_t(int(groups))))
+
     def launch_count(self):
         return int(self.lib.tcb_launch_count(self.ctx))
 

@@ -1,4 +1,7 @@
 // k_g1.cu — G1 kernels (one item per thread), Lagrange coefficients, Commitment::evaluate, roofline probes.
+// The Fp multiply is a real function in this translation unit (fp.cuh, TCB_FP_NOINLINE): with it inlined
+// k_commit_eval spent 71 % of its stall samples on instruction fetch.
+#define TCB_FP_NOINLINE 1
 #include "kern.h"
 #include "scheme.cuh"
 using namespace tcb;
@@ -18,6 +21,14 @@ __global__ void __launch_bounds__(128) k_g1_mul(size_t n, const u8 *sk, const u8
 __global__ void __launch_bounds__(128) k_g1_mul_store(size_t units, const u32 *k, const u8 *pts, Jac1Store *out, u8 *status, size_t per_item) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < units) task_g1_mul_store(i, k, pts, out, status, per_item);
+}
+__global__ void __launch_bounds__(128) k_g1_msm_prep(size_t units, const u32 *k, const u8 *pts, Aff1Store *tab, Glv2Digits *dg, u8 *status, size_t per_item) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < units) task_g1_msm_prep(i, k, pts, tab, dg, status, per_item);
+}
+__global__ void __launch_bounds__(128) k_g1_msm_acc(size_t units, size_t m, size_t G, const Aff1Store *tab, const Glv2Digits *dg, Jac1Store *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < units) task_g1_msm_acc(i, m, G, tab, dg, out);
 }
 __global__ void __launch_bounds__(128) k_g1_sum(size_t n, size_t m, const Jac1Store *terms, u8 *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,7 +94,7 @@ __global__ void __launch_bounds__(256) k_probe_imad(u64 *out, int iters, u32 see
 __global__ void __launch_bounds__(256) k_probe_fpmul(Fp *out, int iters, u64 seed) {
     u64 s = seed + threadIdx.x + (u64)blockIdx.x * 1024;
     Fp a = rand_fp(s, 0), b = rand_fp(s, 0), c = rand_fp(s, 0);
-    for (int it = 0; it < iters; it++) { a = a * c; b = b * c; }
+    for (int it = 0; it < iters; it++) { a = mmul<FpParams>(a, c); b = mmul<FpParams>(b, c); }   // inlined on purpose
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a + b;
 }
 
@@ -113,6 +124,19 @@ void run_g1_mul(cudaStream_t st, size_t n, const u8 *sk, const u8 *pts, u8 *out)
 }
 void run_g1_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item) {
     if (units) k_g1_mul_store<<<grid1(units), 128, 0, st>>>(units, k, pts, (Jac1Store *)terms, status, per_item);
+}
+size_t g1_msm_tab_bytes() { return 2 * sizeof(Aff1Store); }
+size_t g1_msm_dg_bytes() { return sizeof(Glv2Digits); }
+size_t g1_msm_units_per_sm() {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_g1_msm_acc, 128, 0) != cudaSuccess || blocks < 1) blocks = 1;
+    return (size_t)blocks * 128;
+}
+void run_g1_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *tab, void *dg, u8 *status, size_t per_item) {
+    if (units) k_g1_msm_prep<<<grid1(units), 128, 0, st>>>(units, k, pts, (Aff1Store *)tab, (Glv2Digits *)dg, status, per_item);
+}
+void run_g1_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out) {
+    if (units) k_g1_msm_acc<<<grid1(units), 128, 0, st>>>(units, m, G, (const Aff1Store *)tab, (const Glv2Digits *)dg, (Jac1Store *)out);
 }
 void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out) {
     if (n) k_g1_sum<<<grid1(n), 128, 0, st>>>(n, m, (const Jac1Store *)terms, out);

@@ -32,6 +32,16 @@ __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_sum(size_t n, size_t m,
     size_t i = unit_index();
     if (i < n) task_g2_sum<F2>(i, m, terms, out);
 }
+// shared-doubling multi-scalar multiplication (scheme.cuh): per-(item, share) digits + affine table, then
+// one lane pair per (item, group)
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_prep(size_t units, const u32 *k, const u8 *pts, AffStore<F2> *tab, Gls4Digits *dg, u8 *status, size_t per_item) {
+    size_t i = unit_index();
+    if (i < units) task_g2_msm_prep<F2>(i, k, pts, tab, dg, status, per_item);
+}
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_acc(size_t units, size_t m, size_t G, const AffStore<F2> *tab, const Gls4Digits *dg, JacStore<F2> *out) {
+    size_t i = unit_index();
+    if (i < units) task_g2_msm_acc<F2>(i, m, G, tab, dg, out);
+}
 __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_compress(size_t n, const u8 *unc, u8 *out) {
     size_t i = unit_index();
     if (i < n) task_g2_compress<F2>(i, unc, out);
@@ -57,6 +67,19 @@ void run_g2_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *sta
 size_t g2_term_bytes() { return sizeof(JacStore<F2>); }
 void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item) {
     if (units) k_g2_mul_store<<<grid2(units), 128, 0, st>>>(units, k, pts, (JacStore<F2> *)terms, status, per_item);
+}
+size_t g2_msm_tab_bytes() { return 8 * sizeof(AffStore<F2>); }
+size_t g2_msm_dg_bytes() { return sizeof(Gls4Digits); }
+size_t g2_msm_units_per_sm() {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_g2_msm_acc, 128, 0) != cudaSuccess || blocks < 1) blocks = 1;
+    return (size_t)blocks * 64;
+}
+void run_g2_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *tab, void *dg, u8 *status, size_t per_item) {
+    if (units) k_g2_msm_prep<<<grid2(units), 128, 0, st>>>(units, k, pts, (AffStore<F2> *)tab, (Gls4Digits *)dg, status, per_item);
+}
+void run_g2_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out) {
+    if (units) k_g2_msm_acc<<<grid2(units), 128, 0, st>>>(units, m, G, (const AffStore<F2> *)tab, (const Gls4Digits *)dg, (JacStore<F2> *)out);
 }
 void run_g2_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out) {
     if (n) k_g2_sum<<<grid2(n), 128, 0, st>>>(n, m, (const JacStore<F2> *)terms, out);

@@ -1,4 +1,7 @@
 // k_pairing.cu — the pairing-equality kernel (quad engine, quad.cuh) and the on-device self-tests.
+#if defined(TCB_PAIRING_FP_NOINLINE)   // experiment build: Fp multiply / dot2 as functions in the pairing kernel
+#define TCB_FP_NOINLINE 1
+#endif
 #include "kern.h"
 #include "quad.cuh"
 using namespace tcb;

@@ -27,6 +27,11 @@ void run_g2_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *sta
 size_t g2_term_bytes();
 void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item);
 void run_g2_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out);
+size_t g2_msm_tab_bytes();       // per (item, share): 8 affine table entries
+size_t g2_msm_dg_bytes();        // per (item, share): recoded scalar
+size_t g2_msm_units_per_sm();    // resident (item, group) units per SM of k_g2_msm_acc
+void run_g2_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *tab, void *dg, u8 *status, size_t per_item);
+void run_g2_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out);
 // ---- k_g1.cu
 cudaError_t upload_consts_g1(const tcb::Consts &c);
 size_t g1_term_bytes();
@@ -34,6 +39,11 @@ void run_lagrange(cudaStream_t st, size_t n, size_t m, const u8 *xs, u32 *lam, u
 void run_g1_mul(cudaStream_t st, size_t n, const u8 *sk, const u8 *pts, u8 *out);
 void run_g1_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item);
 void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out);
+size_t g1_msm_tab_bytes();
+size_t g1_msm_dg_bytes();
+size_t g1_msm_units_per_sm();
+void run_g1_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *tab, void *dg, u8 *status, size_t per_item);
+void run_g1_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out);
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);

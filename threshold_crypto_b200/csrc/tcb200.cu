@@ -8,8 +8,8 @@
 //   k_hash_g2                   a2     SHA3 -> ChaCha20 -> G2::random -> exact cofactor (lane pairs)
 //   k_sign                      a4     sk * H(m)                                   (lane pairs)
 //   k_lagrange                  a5     lambda_i(0), one thread per (item, share)
-//   k_g2_mul_store / k_g2_sum   a6     per-share terms and their sum (combine_signatures)
-//   k_g1_mul / k_g1_mul_store / k_g1_sum / k_decrypt_finish   a7 (decrypt shares, decrypt)
+//   k_g2_msm_prep / k_g2_msm_acc / k_g2_sum   a6   shared-doubling multi-scalar multiplication (combine_signatures)
+//   k_g1_mul / k_g1_msm_prep / k_g1_msm_acc / k_g1_sum / k_decrypt_finish   a7 (decrypt shares, decrypt)
 //   k_g1_decode / k_commit_eval a8     Commitment::evaluate (Horner)
 //   k_selftest_*, k_probe_*     measurement / self-test
 #include <cuda_runtime.h>
@@ -17,6 +17,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "../../include/tcb200.h"
 #include "kern.h"
 #include "scheme.cuh"
@@ -38,6 +39,8 @@ struct tcb_ctx {
     uint64_t launches = 0;
     int engine = TCB_ENGINE_QUAD;
     int sm_count = 148;
+    size_t msm_groups = 0;          // 0 = auto (pick_groups)
+    bool per_share_terms = false;   // measurement knob (env TCB200_PER_SHARE_TERMS=1): one scalar multiplication per share, no shared doublings
 };
 
 #define CK(call)                                                                                        \
@@ -112,17 +115,71 @@ static int impl_sign(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *sk, cons
     if (n) RUN(run_sign(st, n, sk, msgs, off, h, out));
     return 0;
 }
+// ---- sum_s k_s P_s per item as a shared-doubling multi-scalar multiplication (scheme.cuh, *_msm_*).
+// Groups per item: G partial sums per item trade shared doublings (small G) against parallelism (large G);
+// pick the G that minimises  waves(n G) * (doublings + additions * ceil(m / G)).
+static size_t pick_groups(size_t n, size_t m, size_t units_per_wave, double dbl_cost, double add_cost) {
+    size_t best = 1;
+    double best_cost = 1e300;
+    for (size_t G = 1; G <= m; G++) {
+        size_t per = (m + G - 1) / G;
+        if (G > 1 && (m + G - 2) / (G - 1) == per) continue;          // same depth as G - 1 with more units
+        double waves = (double)((n * G + units_per_wave - 1) / units_per_wave);
+        double cost = waves * (dbl_cost + add_cost * (double)per);
+        if (cost < best_cost * 0.999) { best_cost = cost; best = G; }
+    }
+    return best;
+}
+// out: G Jacobian partial sums per item in `part` (then run_g*_sum(n, G, part, ...))
+static int impl_msm_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
+    if (ctx->per_share_terms) {
+        G = m;
+        part = arena_alloc(ctx, d, n * m * g2_term_bytes());
+        if (!part) return -1;
+        RUN(run_g2_mul_store(st, n * m, k, pts, part, status, m));
+        return 0;
+    }
+    static size_t per_sm = 0;
+    if (!per_sm) per_sm = g2_msm_units_per_sm();
+    G = ctx->msm_groups ? (ctx->msm_groups < m ? ctx->msm_groups : m) : pick_groups(n, m, per_sm * (size_t)ctx->sm_count, 4.8, 8.6);
+    void *tab = arena_alloc(ctx, d, n * m * g2_msm_tab_bytes());
+    void *dg = arena_alloc(ctx, d, n * m * g2_msm_dg_bytes());
+    part = arena_alloc(ctx, d, n * G * g2_term_bytes());
+    if (!tab || !dg || !part) return -1;
+    RUN(run_g2_msm_prep(st, n * m, k, pts, tab, dg, status, m));
+    RUN(run_g2_msm_acc(st, n * G, m, G, tab, dg, part));
+    return 0;
+}
+static int impl_msm_g1(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
+    if (ctx->per_share_terms) {
+        G = m;
+        part = arena_alloc(ctx, d, n * m * g1_term_bytes());
+        if (!part) return -1;
+        RUN(run_g1_mul_store(st, n * m, k, pts, part, status, m));
+        return 0;
+    }
+    static size_t per_sm = 0;
+    if (!per_sm) per_sm = g1_msm_units_per_sm();
+    G = ctx->msm_groups ? (ctx->msm_groups < m ? ctx->msm_groups : m) : pick_groups(n, m, per_sm * (size_t)ctx->sm_count, 7.0, 11.0);
+    void *tab = arena_alloc(ctx, d, n * m * g1_msm_tab_bytes());
+    void *dg = arena_alloc(ctx, d, n * m * g1_msm_dg_bytes());
+    part = arena_alloc(ctx, d, n * G * g1_term_bytes());
+    if (!tab || !dg || !part) return -1;
+    RUN(run_g1_msm_prep(st, n * m, k, pts, tab, dg, status, m));
+    RUN(run_g1_msm_acc(st, n * G, m, G, tab, dg, part));
+    return 0;
+}
 static int impl_combine_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     CK(cudaMemsetAsync(status, 0, n, st));
     if (n == 0) return 0;
     if (t == 0) { CK(cudaMemcpyAsync(out, shares, n * 192, cudaMemcpyDeviceToDevice, st)); return 0; }
     size_t m = t + 1;
     u32 *lam = (u32 *)arena_alloc(ctx, d, n * m * 32);
-    void *terms = arena_alloc(ctx, d, n * m * g2_term_bytes());
-    if (!lam || !terms) return -1;
+    if (!lam) return -1;
     RUN(run_lagrange(st, n, m, x, lam, status));
-    RUN(run_g2_mul_store(st, n * m, lam, shares, terms, status, m));
-    RUN(run_g2_sum(st, n, m, terms, out));
+    void *part; size_t G;
+    if (impl_msm_g2(ctx, d, st, n, m, lam, shares, status, part, G)) return -1;
+    RUN(run_g2_sum(st, n, G, part, out));
     return 0;
 }
 // mode 0: write the combined G1 point; mode 1: xor_with_hash (decrypt)
@@ -137,12 +194,12 @@ static int impl_combine_g1(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n,
     }
     size_t m = t + 1;
     u32 *lam = (u32 *)arena_alloc(ctx, d, n * m * 32);
-    void *terms = arena_alloc(ctx, d, n * m * g1_term_bytes());
-    if (!lam || !terms) return -1;
+    if (!lam) return -1;
     RUN(run_lagrange(st, n, m, x, lam, status));
-    RUN(run_g1_mul_store(st, n * m, lam, shares, terms, status, m));
-    if (mode == 0) RUN(run_g1_sum(st, n, m, terms, out));
-    else RUN(run_decrypt_finish(st, n, m, terms, shares, v, voff, out));
+    void *part; size_t G;
+    if (impl_msm_g1(ctx, d, st, n, m, lam, shares, status, part, G)) return -1;
+    if (mode == 0) RUN(run_g1_sum(st, n, G, part, out));
+    else RUN(run_decrypt_finish(st, n, G, part, shares, v, voff, out));
     return 0;
 }
 static int impl_commit_eval(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
@@ -160,6 +217,7 @@ extern "C" int tcb_init(tcb_ctx **out, const int *device_ids, int n_devices) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return -3;   // no CPU fallback
     tcb_ctx *ctx = new tcb_ctx();
+    { const char *e = getenv("TCB200_PER_SHARE_TERMS"); ctx->per_share_terms = e && e[0] == '1'; }
     Consts C;
     build_consts(C);
     if (n_devices <= 0 || !device_ids) {
@@ -201,6 +259,11 @@ extern "C" const char *tcb_last_error(const tcb_ctx *ctx) { return ctx ? ctx->er
 extern "C" int tcb_set_engine(tcb_ctx *ctx, int engine) {
     if (!ctx || engine != TCB_ENGINE_QUAD) return -2;   // the other engines are debug builds only
     ctx->engine = engine;
+    return 0;
+}
+extern "C" int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups) {
+    if (!ctx) return -2;
+    ctx->msm_groups = groups;
     return 0;
 }
 extern "C" uint64_t tcb_launch_count(const tcb_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -470,11 +533,11 @@ static int lincomb_common(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, c
     FOR_EACH_DEV
         u8 *dsc = up(ctx, d, scalars + 32 * m * s.lo, 32 * m * cnt), *dp = up(ctx, d, pts + pw * m * s.lo, pw * m * cnt);
         u8 *dout = (u8 *)arena_alloc(ctx, d, pw * cnt), *dst = (u8 *)arena_alloc(ctx, d, cnt);
-        void *terms = arena_alloc(ctx, d, cnt * m * (g2 ? g2_term_bytes() : g1_term_bytes()));
-        if (!dsc || !dp || !dout || !dst || !terms) return -1;
-        // canonical little-endian scalars are exactly the limb layout the term kernels read
-        if (g2) { RUN(run_g2_mul_store(st, cnt * m, (const u32 *)dsc, dp, terms, dst, m)); RUN(run_g2_sum(st, cnt, m, terms, dout)); }
-        else { RUN(run_g1_mul_store(st, cnt * m, (const u32 *)dsc, dp, terms, dst, m)); RUN(run_g1_sum(st, cnt, m, terms, dout)); }
+        if (!dsc || !dp || !dout || !dst) return -1;
+        // canonical little-endian scalars are exactly the limb layout the recoding reads
+        void *part; size_t Gp;
+        if (g2) { if (impl_msm_g2(ctx, d, st, cnt, m, (const u32 *)dsc, dp, dst, part, Gp)) return -1; RUN(run_g2_sum(st, cnt, Gp, part, dout)); }
+        else { if (impl_msm_g1(ctx, d, st, cnt, m, (const u32 *)dsc, dp, dst, part, Gp)) return -1; RUN(run_g1_sum(st, cnt, Gp, part, dout)); }
         if (down(ctx, d, out + pw * s.lo, dout, pw * cnt)) return -1;
     END_FOR_EACH_DEV
     return sync_all(ctx);

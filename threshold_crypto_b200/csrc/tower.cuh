@@ -774,23 +774,51 @@ TCB_HD Aff<F2> aff_psi_i(const Aff<F2> &p, int i) {
 // k * P on G2 (P of order r) through the 4-dimensional decomposition k = sum_i d_i X^i,
 // X = |x| = -lambda_psi, i.e. k P = sum_i (-1)^i d_i psi^i(P); 66 doublings + 66 additions from
 // an 8-entry table  T[b3 b2 b1] = P0 + b1 P1 + b2 P2 + b3 P3,  P_i = (-1)^i psi^i(P).
-template <class F2>
-TCB_HDN Jac<F2> jac_mul_gls4(const Aff<F2> &p, const u32 *k_in) {
-    if (p.inf) return jac_inf<F2>();
+// The three pieces (recoding, table, main loop) are separate so that a multi-scalar
+// multiplication can share the 66 doublings between several points (scheme.cuh, *_msm_*).
+//
+// Recoded scalar: digit j (0..65) is a 4-bit nibble, bit 0 = sign of the a0 digit (1 = -1), bits 1-3 = table index.
+struct Gls4Digits {
+    u32 nib[9];
+    u32 flags;   // bit 0: a0 was even (subtract P at the end); bit 1: the point is the point at infinity (skip)
+    TCB_HD u32 digit(int j) const { return (nib[j >> 3] >> ((j & 7) * 4)) & 15u; }
+};
+constexpr int GLS4_L = 65;   // digits 0..GLS4_L
+TCB_HD void gls4_recode(const u32 *k_in, Gls4Digits &dg) {
     u32 k[8];
     for (int i = 0; i < 8; i++) k[i] = k_in[i];
     scalar_reduce(k);
     u64 a[4];
-    u32 ahi[4] = {0, 0, 0, 0};      // bit 64 of a_i (only a0 + 1 can carry)
+    u32 ahi0 = 0;                   // bit 64 of a0 (only a0 + 1 can carry)
     const u64 X = TCB_BLS_X;
     a[0] = divmod_u64(k, X);
     a[1] = divmod_u64(k, X);
     a[2] = divmod_u64(k, X);
     a[3] = (u64)k[0] | ((u64)k[1] << 32);        // k < r < X^4  =>  the last quotient fits 64 bits
     bool even = !(a[0] & 1);
-    if (even) { a[0] += 1; if (a[0] == 0) ahi[0] = 1; }     // make a0 odd; fixed up at the end
-    // table
-    Jac<F2> T[8];
+    if (even) { a[0] += 1; if (a[0] == 0) ahi0 = 1; }     // make a0 odd; fixed up at the end
+    for (int i = 0; i < 9; i++) dg.nib[i] = 0;
+    dg.flags = even ? 1u : 0u;
+    // b0[j] = 2 * bit_{j+1}(a0) - 1 for j < L, b0[L] = +1: sign bit j = !bit_{j+1}(a0)
+    u64 a0s = (a[0] >> 1) | ((u64)ahi0 << 63);       // bits 1..64 of a0 at positions 0..63
+    u64 av[3] = {a[1], a[2], a[3]};
+    u32 avh[3] = {0, 0, 0};
+    for (int j = 0; j <= GLS4_L; j++) {
+        bool neg = j < 64 ? !((a0s >> j) & 1) : (j == 64);   // j = 64: bit 65 of a0 is 0 -> -1 ; j = 65 (top) is +1
+        u32 d = neg ? 1u : 0u;
+        for (int t = 0; t < 3; t++) {
+            u32 bit = (u32)(av[t] & 1);
+            d |= bit << (t + 1);
+            // a = floor(a / 2) - floor(b / 2),  b = bit * (+1 | -1):  b = -1 -> floor(-1/2) = -1 -> +1
+            av[t] = (av[t] >> 1) | ((u64)avh[t] << 63);
+            avh[t] = 0;
+            if (bit && neg && j < GLS4_L) { av[t] += 1; if (av[t] == 0) avh[t] = 1; }
+        }
+        dg.nib[j >> 3] |= d << ((j & 7) * 4);
+    }
+}
+template <class F2>
+TCB_HD void gls4_table(const Aff<F2> &p, Jac<F2> *T) {
     Aff<F2> P1 = aff_psi_i(p, 1), P2 = aff_psi_i(p, 2), P3 = aff_psi_i(p, 3);
     P1.y = -P1.y; P3.y = -P3.y;
     T[0] = jac_from_aff(p);
@@ -801,44 +829,41 @@ TCB_HDN Jac<F2> jac_mul_gls4(const Aff<F2> &p, const u32 *k_in) {
     T[5] = jac_add_mixed(T[1], P3);
     T[6] = jac_add_mixed(T[2], P3);
     T[7] = jac_add_mixed(T[3], P3);
-    // regular recoding, digits produced LSB first: sign[j] of a0, idx bits of a1..a3
-    const int L = 65;               // digits 0..L
-    u64 sgn_lo = 0; u32 sgn_hi = 0;   // bit j set  <=>  b0[j] = -1
-    u64 i1_lo = 0, i2_lo = 0, i3_lo = 0; u32 i1_hi = 0, i2_hi = 0, i3_hi = 0;
-    {
-        // b0[j] = 2 * bit_{j+1}(a0) - 1 for j < L, b0[L] = +1
-        u64 a0s = (a[0] >> 1) | ((u64)ahi[0] << 63);       // bits 1..64 of a0 at positions 0..63
-        sgn_lo = ~a0s;                                       // -1 where bit_{j+1} == 0, j = 0..63
-        sgn_hi = 1u;                                         // j = 64: bit 65 of a0 is 0 -> -1 ; j = 65 (top) is +1
-        u64 av[3] = {a[1], a[2], a[3]};
-        u32 avh[3] = {0, 0, 0};
-        u64 *ilo[3] = {&i1_lo, &i2_lo, &i3_lo};
-        u32 *ihi[3] = {&i1_hi, &i2_hi, &i3_hi};
-        for (int j = 0; j <= L; j++) {
-            bool neg = j < 64 ? ((sgn_lo >> j) & 1) : (j == 64 ? (sgn_hi & 1u) : false);
-            for (int t = 0; t < 3; t++) {
-                u32 bit = (u32)(av[t] & 1);
-                if (j < 64) *ilo[t] |= (u64)bit << j; else *ihi[t] |= bit << (j - 64);
-                // a = floor(a / 2) - floor(b / 2),  b = bit * (+1 | -1):  b = -1 -> floor(-1/2) = -1 -> +1
-                av[t] = (av[t] >> 1) | ((u64)avh[t] << 63);
-                avh[t] = 0;
-                if (bit && neg && j < L) { av[t] += 1; if (av[t] == 0) avh[t] = 1; }
-            }
-        }
-    }
+}
+template <class F2>
+TCB_HDN Jac<F2> jac_mul_gls4(const Aff<F2> &p, const u32 *k_in) {
+    if (p.inf) return jac_inf<F2>();
+    Gls4Digits dg;
+    gls4_recode(k_in, dg);
+    Jac<F2> T[8];
+    gls4_table(p, T);
     Jac<F2> acc = jac_inf<F2>();
-    for (int j = L; j >= 0; j--) {
+    for (int j = GLS4_L; j >= 0; j--) {
         acc = jac_dbl(acc);
-        bool neg = j < 64 ? ((sgn_lo >> j) & 1) : (j == 64 ? (sgn_hi & 1u) : false);
-        u32 b1 = j < 64 ? (u32)((i1_lo >> j) & 1) : ((i1_hi >> (j - 64)) & 1u);
-        u32 b2 = j < 64 ? (u32)((i2_lo >> j) & 1) : ((i2_hi >> (j - 64)) & 1u);
-        u32 b3 = j < 64 ? (u32)((i3_lo >> j) & 1) : ((i3_hi >> (j - 64)) & 1u);
-        Jac<F2> t = T[b1 | (b2 << 1) | (b3 << 2)];
-        if (neg) t.y = -t.y;
+        u32 d = dg.digit(j);
+        Jac<F2> t = T[d >> 1];
+        if (d & 1) t.y = -t.y;
         acc = jac_add(acc, t);
     }
-    if (even) { Aff<F2> np = p; np.y = -p.y; acc = jac_add_mixed(acc, np); }
+    if (dg.flags & 1) { Aff<F2> np = p; np.y = -p.y; acc = jac_add_mixed(acc, np); }
     return acc;
+}
+// Simultaneous conversion of N Jacobian points to affine with ONE field inversion (Montgomery's
+// trick).  None of the inputs may be the point at infinity.
+template <class F, int N>
+TCB_HD void jac_batch_to_aff(const Jac<F> *in, Aff<F> *out) {
+    F pre[N];
+    pre[0] = in[0].z;
+    for (int i = 1; i < N; i++) pre[i] = pre[i - 1] * in[i].z;
+    F acc = inv(pre[N - 1]);
+    for (int i = N - 1; i >= 0; i--) {
+        F zi = i ? acc * pre[i - 1] : acc;
+        if (i) acc = acc * in[i].z;
+        F zi2 = sqr(zi);
+        out[i].x = in[i].x * zi2;
+        out[i].y = in[i].y * (zi2 * zi);
+        out[i].inf = false;
+    }
 }
 // q (8 limbs) := q / d for a 128-bit divisor d = (dhi, dlo) with its top bit set; remainder in (rhi, rlo)
 TCB_HD void divmod_u128(u32 *q, u64 dhi, u64 dlo, u64 &rhi, u64 &rlo) {
@@ -854,8 +879,14 @@ TCB_HD void divmod_u128(u32 *q, u64 dhi, u64 dlo, u64 &rhi, u64 &rlo) {
 }
 // k * P on G1 (P of order r): k = a + b X^2 and [X^2]P = -phi(P), phi(x, y) = (beta x, y);
 // regular recoding on (a, b): 130 doublings + 130 additions from {P0, P0 + P1}, P1 = -phi(P).
-TCB_HDN Jac<Fp> jac_mul_glv2(const Aff<Fp> &p, const u32 *k_in) {
-    if (p.inf) return jac_inf<Fp>();
+// Recoded scalar: digit j (0..129) is 2 bits, bit 0 = sign (1 = -1), bit 1 = table index.
+struct Glv2Digits {
+    u32 w[9];
+    u32 flags;   // bit 0: a was even (subtract P at the end); bit 1: point at infinity (skip)
+    TCB_HD u32 digit(int j) const { return (w[j >> 4] >> ((j & 15) * 2)) & 3u; }
+};
+constexpr int GLV2_L = 129;   // digits 0..GLV2_L
+TCB_HD void glv2_recode(const u32 *k_in, Glv2Digits &dg) {
     u32 k[8];
     for (int i = 0; i < 8; i++) k[i] = k_in[i];
     scalar_reduce(k);
@@ -867,37 +898,39 @@ TCB_HDN Jac<Fp> jac_mul_glv2(const Aff<Fp> &p, const u32 *k_in) {
     bool even = !(alo & 1);
     u32 atop = 0;
     if (even) { alo += 1; if (alo == 0) { ahi += 1; if (ahi == 0) atop = 1; } }
+    for (int i = 0; i < 9; i++) dg.w[i] = 0;
+    dg.flags = even ? 1u : 0u;
+    // bits 1..129 of a at positions 0..128; sign bit j = !bit_{j+1}(a), top digit +1
+    u64 s0 = (alo >> 1) | (ahi << 63), s1 = (ahi >> 1) | ((u64)atop << 63);
+    u64 b0 = blo, b1 = bhi; u32 b2 = 0;
+    for (int j = 0; j <= GLV2_L; j++) {
+        bool neg = j < 64 ? !((s0 >> j) & 1) : (j < 128 ? !((s1 >> (j - 64)) & 1) : (j == 128));
+        u32 bit = (u32)(b0 & 1);
+        dg.w[j >> 4] |= ((neg ? 1u : 0u) | (bit << 1)) << ((j & 15) * 2);
+        b0 = (b0 >> 1) | (b1 << 63); b1 = (b1 >> 1) | ((u64)b2 << 63); b2 = 0;
+        if (bit && neg && j < GLV2_L) { b0 += 1; if (b0 == 0) { b1 += 1; if (b1 == 0) b2 = 1; } }
+    }
+}
+TCB_HD Aff<Fp> glv2_p1(const Aff<Fp> &p) {
     Aff<Fp> P1;
     P1.x = p.x * CONSTS().beta; P1.y = -p.y; P1.inf = false;
+    return P1;
+}
+TCB_HDN Jac<Fp> jac_mul_glv2(const Aff<Fp> &p, const u32 *k_in) {
+    if (p.inf) return jac_inf<Fp>();
+    Glv2Digits dg;
+    glv2_recode(k_in, dg);
     Jac<Fp> T0 = jac_from_aff(p);
-    Jac<Fp> T1 = jac_add_mixed(T0, P1);
-    const int L = 129;   // digits 0..L
-    // sign bits (b0[j] = -1) and index bits for j = 0..L, in three words
-    u64 sg[3] = {0, 0, 0}, ix[3] = {0, 0, 0};
-    {
-        // bits 1..129 of a at positions 0..128
-        u64 s0 = (alo >> 1) | (ahi << 63), s1 = (ahi >> 1) | ((u64)atop << 63);
-        sg[0] = ~s0; sg[1] = ~s1; sg[2] = 1u;      // j = 128: bit 129 of a is 0 -> -1 ; j = 129 (top) is +1
-        u64 b0 = blo, b1 = bhi; u32 b2 = 0;
-        for (int j = 0; j <= L; j++) {
-            bool neg = (sg[j >> 6] >> (j & 63)) & 1;
-            if (j == L) neg = false;
-            u32 bit = (u32)(b0 & 1);
-            ix[j >> 6] |= (u64)bit << (j & 63);
-            b0 = (b0 >> 1) | (b1 << 63); b1 = (b1 >> 1) | ((u64)b2 << 63); b2 = 0;
-            if (bit && neg && j < L) { b0 += 1; if (b0 == 0) { b1 += 1; if (b1 == 0) b2 = 1; } }
-        }
-    }
+    Jac<Fp> T1 = jac_add_mixed(T0, glv2_p1(p));
     Jac<Fp> acc = jac_inf<Fp>();
-    for (int j = L; j >= 0; j--) {
+    for (int j = GLV2_L; j >= 0; j--) {
         acc = jac_dbl(acc);
-        bool neg = (j < L) && ((sg[j >> 6] >> (j & 63)) & 1);
-        bool one = (ix[j >> 6] >> (j & 63)) & 1;
-        Jac<Fp> t = one ? T1 : T0;
-        if (neg) t.y = -t.y;
+        u32 d = dg.digit(j);
+        Jac<Fp> t = (d & 2) ? T1 : T0;
+        if (d & 1) t.y = -t.y;
         acc = jac_add(acc, t);
     }
-    if (even) { Aff<Fp> np = p; np.y = -p.y; acc = jac_add_mixed(acc, np); }
+    if (dg.flags & 1) { Aff<Fp> np = p; np.y = -p.y; acc = jac_add_mixed(acc, np); }
     return acc;
 }
 
