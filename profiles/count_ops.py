@@ -37,10 +37,13 @@ out["hash_g2_macs_per_item"] = count(lambda: E.hash_g2_batch(msgs)) / n
 out["sign_g2_macs_per_item"] = count(lambda: E.sign_g2_batch(sk, h)) / n
 nc, t = 8, 10
 xs, sh, master = cases.make_combine_batch(O, nc, t, 77, group=2, extra=21)
+E.set_msm_groups(1)      # what pick_groups chooses for 2^14 items (one partial sum per item)
 out["combine_g2_t10_macs_per_item"] = count(lambda: E.combine_g2_batch(nc, t, xs, sh)) / nc
 nc, t = 2, 64
 xs, sh, master = cases.make_combine_batch(O, nc, t, 78, group=1, extra=10)
+E.set_msm_groups(13)     # what pick_groups chooses for 2^12 items of 65 shares
 out["combine_g1_t64_macs_per_item"] = count(lambda: E.combine_g1_batch(nc, t, xs, sh)) / nc
+E.set_msm_groups(0)
 rng = np.random.default_rng(1)
 coeff = conftest.rand_fr(rng, 64)
 comm = O.g1_mul_gen_batch(coeff)

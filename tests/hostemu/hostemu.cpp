@@ -109,7 +109,7 @@ extern "C" int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const u8 *sk, u8 *out) 
     return 0;
 }
 extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
-    std::vector<Jac1Store> tab(deg + 1);
+    std::vector<Aff1Store> tab(deg + 1);
     for (size_t c = 0; c <= deg; c++) task_g1_decode(c, coeff, tab.data());
     for (size_t i = 0; i < n; i++) task_commit_eval(i, deg, tab.data(), x, out);
     return 0;

@@ -44,11 +44,12 @@ __global__ void __launch_bounds__(128) k_decrypt_finish(size_t n, size_t m, cons
     else { bool ok = true; g = load_g1(first_shares + 96 * i, ok); }
     xor_with_hash(out + voff[i], g, v + voff[i], (size_t)(voff[i + 1] - voff[i]));
 }
-__global__ void __launch_bounds__(128) k_g1_decode(size_t n, const u8 *pts, Jac1Store *out) {
+__global__ void __launch_bounds__(128) k_g1_decode(size_t n, const u8 *pts, Aff1Store *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) task_g1_decode(i, pts, out);
 }
-__global__ void __launch_bounds__(128) k_commit_eval(size_t n, size_t deg, const Jac1Store *coeff, const u8 *x, u8 *out) {
+// 4 blocks/SM (<= 128 registers): 2^16 evaluation points fit one wave of 148 x 512 threads
+__global__ void __launch_bounds__(128, 4) k_commit_eval(size_t n, size_t deg, const Aff1Store *coeff, const u8 *x, u8 *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) task_commit_eval(i, deg, coeff, x, out);
 }
@@ -145,10 +146,10 @@ void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, 
     if (n) k_decrypt_finish<<<grid1(n), 128, 0, st>>>(n, m, (const Jac1Store *)terms, first_shares, v, voff, out);
 }
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab) {
-    if (n) k_g1_decode<<<grid1(n), 128, 0, st>>>(n, pts, (Jac1Store *)tab);
+    if (n) k_g1_decode<<<grid1(n), 128, 0, st>>>(n, pts, (Aff1Store *)tab);
 }
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out) {
-    if (n) k_commit_eval<<<grid1(n), 128, 0, st>>>(n, deg, (const Jac1Store *)tab, x, out);
+    if (n) k_commit_eval<<<grid1(n), 128, 0, st>>>(n, deg, (const Aff1Store *)tab, x, out);
 }
 void run_encrypt_uv(cudaStream_t st, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out) {
     if (n) k_encrypt_uv<<<grid1(n), 128, 0, st>>>(n, pk, r, msgs, off, u_out, v_out);

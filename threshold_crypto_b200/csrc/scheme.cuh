@@ -234,20 +234,6 @@ TCB_HD bool bcast_flag(bool v, int src) {
 #endif
     return v;
 }
-// a / 2 mod p (valid on Montgomery representatives as well)
-TCB_HD Fp fp_half(const Fp &a) {
-    u32 mask = (a.l[0] & 1u) ? 0xffffffffu : 0u;
-    u32 t[12], hi;
-    add_cc(t[0], a.l[0], FpParams::mod(0) & mask);
-#pragma unroll
-    for (int i = 1; i < 12; i++) addc_cc(t[i], a.l[i], FpParams::mod(i) & mask);
-    addc(hi, 0, 0);
-    Fp r;
-#pragma unroll
-    for (int i = 0; i < 11; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
-    r.l[11] = (t[11] >> 1) | (hi << 31);
-    return r;
-}
 // EXTERNAL pairing 0.16 G2::random (A2, A3): x = Fq2::random, greatest = next_u32() % 2,
 // y = sqrt(x^3 + b) picked by (y < -y) ^ greatest, multiplied by the exact cofactor h2, retry on
 // no root / zero.  The candidates are consumed from the ChaCha stream in the reference's order;
@@ -467,11 +453,8 @@ TCB_HD void task_g2_msm_prep(size_t u, const u32 *k_limbs, const u8 *pts_g2, Aff
     gls4_recode(k_limbs + 8 * u, dg);
     if (p.inf) dg.flags |= 2u;
     else {
-        Jac<F2> T[8];
         Aff<F2> A[8];
-        gls4_table(p, T);
-        A[0] = p;
-        jac_batch_to_aff<F2, 7>(T + 1, A + 1);
+        gls4_table_affine(p, A);
         for (int e = 0; e < 8; e++) { A[e].x.store(tab[8 * u + e].x); A[e].y.store(tab[8 * u + e].y); }
     }
     if (is_writer<F2>()) {
@@ -566,13 +549,9 @@ TCB_HD void task_g1_msm_prep(size_t u, const u32 *k_limbs, const u8 *pts_g1, Aff
     glv2_recode(k_limbs + 8 * u, dg);
     if (p.inf) dg.flags |= 2u;
     else {
-        // P + P1, P1 = (beta x, -y): lambda = -2y / ((beta - 1) x)  (x != 0 for a point of order r)
-        Fp bx = p.x * CONSTS().beta;
-        Fp lam = -dbl(p.y) * fp_inv(bx - p.x);
-        Fp x3 = sqr(lam) - p.x - bx;
-        Fp y3 = lam * (p.x - x3) - p.y;
+        Aff<Fp> t1 = glv2_t1_affine(p);
         tab[2 * u].x = p.x; tab[2 * u].y = p.y;
-        tab[2 * u + 1].x = x3; tab[2 * u + 1].y = y3;
+        tab[2 * u + 1].x = t1.x; tab[2 * u + 1].y = t1.y;
     }
     dgs[u] = dg;
     if (!ok) status[u / per_item] = 3;
@@ -616,17 +595,33 @@ TCB_HD void task_g1_msm_acc(size_t w, size_t m, size_t G, const Aff1Store *tab, 
     }
     out[w].x = acc.x; out[w].y = acc.y; out[w].z = acc.z;
 }
-// a8: Commitment::evaluate (src/poly.rs:497-508): Horner, acc = acc * x + C_k
-TCB_HD void task_commit_eval(size_t i, size_t deg, const Jac1Store *coeff, const u8 *x_fr, u8 *out_g1) {
+// a8: Commitment::evaluate (src/poly.rs:497-508): Horner, acc = acc * x + C_k.  The coefficient table is
+// decoded once (affine, Montgomery form; the point at infinity is stored as (0, 0), which is not on the
+// curve) so that "+ C_k" is a mixed addition; "acc * x" skips the leading zero bits of x (the indices
+// are small integers in the reference's use: public_key_share(i) = evaluate(i + 1), src/lib.rs:596-600).
+TCB_HD Aff<Fp> aff1_load(const Aff1Store &e) {
+    Aff<Fp> t;
+    t.x = e.x; t.y = e.y;
+    t.inf = e.x.is_zero() && e.y.is_zero();
+    return t;
+}
+TCB_HD void task_commit_eval(size_t i, size_t deg, const Aff1Store *coeff, const u8 *x_fr, u8 *out_g1) {
     u32 k[8];
     load_scalar_le(k, x_fr + 32 * i);
-    Jac<Fp> acc;
-    acc.x = coeff[deg].x; acc.y = coeff[deg].y; acc.z = coeff[deg].z;
+    int top = -1;                                  // index of the leading one of x
+    for (int b = 255; b >= 0; b--)
+        if ((k[b >> 5] >> (b & 31)) & 1) { top = b; break; }
+    Jac<Fp> acc = jac_from_aff(aff1_load(coeff[deg]));
     for (size_t c = deg; c-- > 0;) {
-        acc = jac_mul_jac<Fp, 8>(acc, k);
-        Jac<Fp> ck;
-        ck.x = coeff[c].x; ck.y = coeff[c].y; ck.z = coeff[c].z;
-        acc = jac_add(acc, ck);
+        if (top < 0) acc = jac_inf<Fp>();
+        else {
+            Jac<Fp> base = acc;
+            for (int b = top - 1; b >= 0; b--) {
+                acc = jac_dbl(acc);
+                if ((k[b >> 5] >> (b & 31)) & 1) acc = jac_add(acc, base);
+            }
+        }
+        acc = jac_add_mixed(acc, aff1_load(coeff[c]));
     }
     store_g1(out_g1 + 96 * i, jac_to_aff(acc));
 }
@@ -644,10 +639,11 @@ TCB_HD void task_encrypt_uv(size_t i, const u8 *pk_g1, const u8 *r_fr, const u8 
     Aff<Fp> s = jac_to_aff(jac_mul_glv2(pk, k));
     xor_with_hash(v_out + off[i], s, msgs + off[i], (size_t)(off[i + 1] - off[i]));
 }
-TCB_HD void task_g1_decode(size_t i, const u8 *pts_g1, Jac1Store *out) {
+TCB_HD void task_g1_decode(size_t i, const u8 *pts_g1, Aff1Store *out) {
     bool ok = true;
-    Jac<Fp> p = jac_from_aff(load_g1(pts_g1 + 96 * i, ok));
-    out[i].x = p.x; out[i].y = p.y; out[i].z = p.z;
+    Aff<Fp> p = load_g1(pts_g1 + 96 * i, ok);
+    out[i].x = p.inf ? Fp::zero() : p.x;
+    out[i].y = p.inf ? Fp::zero() : p.y;
 }
 
 // ----------------------------------------------------------------------------- §8(f) row 1: batched point (de)compression
