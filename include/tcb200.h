@@ -49,6 +49,11 @@ int tcb_set_engine(tcb_ctx *ctx, int engine);
 /* Tuning knob of the multi-scalar multiplication behind combine / decrypt / lincomb: partial sums per
  * item (shared doublings vs. parallelism).  0 (default) = chosen per call from the batch shape. */
 int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups);
+/* Algorithm of that multi-scalar multiplication: 0 (default) Straus with shared doublings and mixed additions from
+ * affine per-share tables, 1 batch-affine pairwise tree + Horner (28 % fewer multiplications, but slower on B200:
+ * bound by global-memory latency at 2 warps per scheduler), 2 one scalar multiplication per share.  Same outputs;
+ * 1 and 2 exist for measurement. */
+int tcb_set_msm_algo(tcb_ctx *ctx, int algo);
 /* number of kernel launches issued through ctx since tcb_init (bench.py's gpu_launches) */
 uint64_t tcb_launch_count(const tcb_ctx *ctx);
 

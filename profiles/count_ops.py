@@ -41,7 +41,7 @@ E.set_msm_groups(1)      # what pick_groups chooses for 2^14 items (one partial 
 out["combine_g2_t10_macs_per_item"] = count(lambda: E.combine_g2_batch(nc, t, xs, sh)) / nc
 nc, t = 2, 64
 xs, sh, master = cases.make_combine_batch(O, nc, t, 78, group=1, extra=10)
-E.set_msm_groups(13)     # what pick_groups chooses for 2^12 items of 65 shares
+E.set_msm_groups(13)     # what pick_groups chooses for 2^12 items of 65 shares (3 blocks/SM)
 out["combine_g1_t64_macs_per_item"] = count(lambda: E.combine_g1_batch(nc, t, xs, sh)) / nc
 E.set_msm_groups(0)
 rng = np.random.default_rng(1)

@@ -49,20 +49,31 @@ extern "C" int tcb_sign_g2_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *h,
 static size_t g_groups = 2;
 extern "C" void tcb_emu_set_groups(size_t g) { g_groups = g ? g : 1; }
 extern "C" int tcb_set_msm_groups(tcb_ctx *, size_t g) { g_groups = g ? g : 2; return 0; }
+static int g_algo = 0;
+extern "C" int tcb_set_msm_algo(tcb_ctx *, int a) { g_algo = a; return 0; }
+template <class M, class JS>
+static void msm_acc_ba(size_t n, size_t m, size_t G, const typename M::PS *tab, const typename M::DG *dg, JS *part) {
+    size_t cnt_max = (m + G - 1) / G;
+    std::vector<typename M::PS> a(n * G * ba_points_per_unit<M>(cnt_max)), b(a.size());
+    std::vector<typename M::FS> pre(n * G * ba_prefix_per_unit<M>(cnt_max));
+    for (size_t w = 0; w < n * G; w++) task_msm_acc_ba<M>(w, m, G, tab, dg, a.data(), b.data(), pre.data(), cnt_max, part);
+}
 static void g2_msm(size_t n, size_t m, const u32 *k, const u8 *pts, u8 *out, u8 *status) {
     size_t G = g_groups < m ? g_groups : m;
     std::vector<AffStore<Fp2>> tab(n * m * 8);
     std::vector<Gls4Digits> dg(n * m);
     std::vector<JacStore<Fp2>> part(n * G);
     for (size_t u = 0; u < n * m; u++) task_g2_msm_prep<Fp2>(u, k, pts, tab.data(), dg.data(), status, m);
-    for (size_t w = 0; w < n * G; w++) task_g2_msm_acc<Fp2>(w, m, G, tab.data(), dg.data(), part.data());
+    if (g_algo == 1) msm_acc_ba<MsmG2<Fp2>>(n, m, G, tab.data(), dg.data(), part.data());
+    else for (size_t w = 0; w < n * G; w++) task_g2_msm_acc<Fp2>(w, m, G, tab.data(), dg.data(), part.data());
     for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, G, part.data(), out);
 }
 static void g1_msm(size_t n, size_t m, const u32 *k, const u8 *pts, Jac1Store *part, size_t G, u8 *status) {
     std::vector<Aff1Store> tab(n * m * 2);
     std::vector<Glv2Digits> dg(n * m);
     for (size_t u = 0; u < n * m; u++) task_g1_msm_prep(u, k, pts, tab.data(), dg.data(), status, m);
-    for (size_t w = 0; w < n * G; w++) task_g1_msm_acc(w, m, G, tab.data(), dg.data(), part);
+    if (g_algo == 1) msm_acc_ba<MsmG1>(n, m, G, tab.data(), dg.data(), part);
+    else for (size_t w = 0; w < n * G; w++) task_g1_msm_acc(w, m, G, tab.data(), dg.data(), part);
 }
 extern "C" int tcb_combine_g2_batch(tcb_ctx *, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     memset(status, 0, n);

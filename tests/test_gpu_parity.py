@@ -137,6 +137,8 @@ def test_msm_groupings_and_edges(gpu_engine, O):
     with the automatic choice: zero / one / r-1 scalars, infinity shares, repeated and cancelling pairs."""
     E = gpu_engine
     try:
+      for algo in (0, 1, 2):
+        E.set_msm_algo(algo)
         for g in (1, 2, 3, 1000, 0):
             E.set_msm_groups(g)
             cases.check_msm(E, O, n=5, m=7, seed=30 + g % 7)
@@ -148,6 +150,7 @@ def test_msm_groupings_and_edges(gpu_engine, O):
             assert np.array_equal(out, master) and not st.any()
     finally:
         E.set_msm_groups(0)
+        E.set_msm_algo(0)
 
 
 def test_multi_device_ctx_matches_single(O):

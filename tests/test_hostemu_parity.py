@@ -38,14 +38,17 @@ def test_hostemu_golden(emu, golden):
 def test_hostemu_msm_groupings(emu, O):
     """Shared-doubling MSM with 1, 2 and m groups per item (m groups = one share per unit)."""
     try:
-        for g in (1, 2, 64):
-            emu.set_msm_groups(g)
-            cases.check_msm(emu, O, n=3, m=5, seed=21 + g)
-            x, s, master = cases.make_combine_batch(O, 2, 3, 40 + g, group=2)
-            out, st = emu.combine_g2_batch(2, 3, x, s)
-            assert np.array_equal(out, master) and not st.any()
+        for algo in (0, 1):          # Straus with mixed additions, batch-affine tree
+            emu.set_msm_algo(algo)
+            for g in (1, 2, 64):
+                emu.set_msm_groups(g)
+                cases.check_msm(emu, O, n=3, m=5, seed=21 + g)
+                x, s, master = cases.make_combine_batch(O, 2, 3, 40 + g, group=2)
+                out, st = emu.combine_g2_batch(2, 3, x, s)
+                assert np.array_equal(out, master) and not st.any()
     finally:
         emu.set_msm_groups(0)
+        emu.set_msm_algo(0)
 
 
 def test_binary_gcd_inverse_and_legendre_symbol(emu):

@@ -86,6 +86,10 @@ class Engine:
         """Partial sums per item of the shared-doubling multi-scalar multiplication (0 = auto)."""
         self._ck(self.lib.tcb_set_msm_groups(self.ctx, C.c_size_t(int(groups))))
 
+    def set_msm_algo(self, algo):
+        """0 Straus / shared doublings (default), 1 batch-affine tree, 2 one multiplication per share."""
+        self._ck(self.lib.tcb_set_msm_algo(self.ctx, int(algo)))
+
     def launch_count(self):
         return int(self.lib.tcb_launch_count(self.ctx))
 

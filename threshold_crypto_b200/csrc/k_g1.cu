@@ -30,6 +30,17 @@ __global__ void __launch_bounds__(128) k_g1_msm_acc(size_t units, size_t m, size
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < units) task_g1_msm_acc(i, m, G, tab, dg, out);
 }
+__global__ void __launch_bounds__(128) k_g1_msm_acc_ba(size_t units, size_t m, size_t G, const Aff1Store *tab, const Glv2Digits *dg,
+                                                       Aff1Store *buf_a, Aff1Store *buf_b, Fp *prefix, size_t cnt_max, Jac1Store *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < units) task_msm_acc_ba<MsmG1>(i, m, G, tab, dg, buf_a, buf_b, prefix, cnt_max, out);
+}
+// experiment (tcb_set_msm_algo 3): the G2 accumulation with ONE item per thread (unsliced Fp2, multiplies as calls)
+// instead of one per lane pair; same tables, digits and outputs as k_g2_msm_acc
+__global__ void __launch_bounds__(128) k_g2_msm_acc_thread(size_t units, size_t m, size_t G, const AffStore<Fp2> *tab, const Gls4Digits *dg, JacStore<Fp2> *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < units) task_g2_msm_acc<Fp2>(i, m, G, tab, dg, out);
+}
 __global__ void __launch_bounds__(128) k_g1_sum(size_t n, size_t m, const Jac1Store *terms, u8 *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) store_g1(out + 96 * i, g1_sum(i, m, terms));
@@ -138,6 +149,25 @@ void run_g1_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts,
 }
 void run_g1_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out) {
     if (units) k_g1_msm_acc<<<grid1(units), 128, 0, st>>>(units, m, G, (const Aff1Store *)tab, (const Glv2Digits *)dg, (Jac1Store *)out);
+}
+size_t g2_msm_thread_units_per_sm() {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_g2_msm_acc_thread, 128, 0) != cudaSuccess || blocks < 1) blocks = 1;
+    return (size_t)blocks * 128;
+}
+void run_g2_msm_acc_thread(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out) {
+    if (units) k_g2_msm_acc_thread<<<grid1(units), 128, 0, st>>>(units, m, G, (const AffStore<Fp2> *)tab, (const Gls4Digits *)dg, (JacStore<Fp2> *)out);
+}
+size_t g1_msm_ba_units_per_sm() {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_g1_msm_acc_ba, 128, 0) != cudaSuccess || blocks < 1) blocks = 1;
+    return (size_t)blocks * 128;
+}
+size_t g1_msm_ba_point_bytes(size_t cnt_max) { return ba_points_per_unit<MsmG1>(cnt_max) * sizeof(Aff1Store); }
+size_t g1_msm_ba_prefix_bytes(size_t cnt_max) { return ba_prefix_per_unit<MsmG1>(cnt_max) * sizeof(Fp); }
+void run_g1_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *buf_a, void *buf_b, void *prefix, size_t cnt_max, void *out) {
+    if (units) k_g1_msm_acc_ba<<<grid1(units), 128, 0, st>>>(units, m, G, (const Aff1Store *)tab, (const Glv2Digits *)dg, (Aff1Store *)buf_a,
+                                                            (Aff1Store *)buf_b, (Fp *)prefix, cnt_max, (Jac1Store *)out);
 }
 void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out) {
     if (n) k_g1_sum<<<grid1(n), 128, 0, st>>>(n, m, (const Jac1Store *)terms, out);

@@ -42,6 +42,11 @@ __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_acc(size_t units, s
     size_t i = unit_index();
     if (i < units) task_g2_msm_acc<F2>(i, m, G, tab, dg, out);
 }
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_acc_ba(size_t units, size_t m, size_t G, const AffStore<F2> *tab, const Gls4Digits *dg,
+                                                                   AffStore<F2> *buf_a, AffStore<F2> *buf_b, Fp2c *prefix, size_t cnt_max, JacStore<F2> *out) {
+    size_t i = unit_index();
+    if (i < units) task_msm_acc_ba<MsmG2<F2>>(i, m, G, tab, dg, buf_a, buf_b, prefix, cnt_max, out);
+}
 __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_compress(size_t n, const u8 *unc, u8 *out) {
     size_t i = unit_index();
     if (i < n) task_g2_compress<F2>(i, unc, out);
@@ -80,6 +85,17 @@ void run_g2_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts,
 }
 void run_g2_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out) {
     if (units) k_g2_msm_acc<<<grid2(units), 128, 0, st>>>(units, m, G, (const AffStore<F2> *)tab, (const Gls4Digits *)dg, (JacStore<F2> *)out);
+}
+size_t g2_msm_ba_units_per_sm() {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_g2_msm_acc_ba, 128, 0) != cudaSuccess || blocks < 1) blocks = 1;
+    return (size_t)blocks * 64;
+}
+size_t g2_msm_ba_point_bytes(size_t cnt_max) { return ba_points_per_unit<MsmG2<F2>>(cnt_max) * sizeof(AffStore<F2>); }
+size_t g2_msm_ba_prefix_bytes(size_t cnt_max) { return ba_prefix_per_unit<MsmG2<F2>>(cnt_max) * sizeof(Fp2c); }
+void run_g2_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *buf_a, void *buf_b, void *prefix, size_t cnt_max, void *out) {
+    if (units) k_g2_msm_acc_ba<<<grid2(units), 128, 0, st>>>(units, m, G, (const AffStore<F2> *)tab, (const Gls4Digits *)dg, (AffStore<F2> *)buf_a,
+                                                            (AffStore<F2> *)buf_b, (Fp2c *)prefix, cnt_max, (JacStore<F2> *)out);
 }
 void run_g2_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out) {
     if (n) k_g2_sum<<<grid2(n), 128, 0, st>>>(n, m, (const JacStore<F2> *)terms, out);

@@ -32,6 +32,11 @@ size_t g2_msm_dg_bytes();        // per (item, share): recoded scalar
 size_t g2_msm_units_per_sm();    // resident (item, group) units per SM of k_g2_msm_acc
 void run_g2_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *tab, void *dg, u8 *status, size_t per_item);
 void run_g2_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out);
+// batch-affine accumulation: scratch per unit = 2 point buffers + prefix products for up to cnt_max shares per unit
+size_t g2_msm_ba_units_per_sm();
+size_t g2_msm_ba_point_bytes(size_t cnt_max);
+size_t g2_msm_ba_prefix_bytes(size_t cnt_max);
+void run_g2_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *buf_a, void *buf_b, void *prefix, size_t cnt_max, void *out);
 // ---- k_g1.cu
 cudaError_t upload_consts_g1(const tcb::Consts &c);
 size_t g1_term_bytes();
@@ -44,6 +49,12 @@ size_t g1_msm_dg_bytes();
 size_t g1_msm_units_per_sm();
 void run_g1_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *tab, void *dg, u8 *status, size_t per_item);
 void run_g1_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out);
+size_t g2_msm_thread_units_per_sm();
+void run_g2_msm_acc_thread(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out);
+size_t g1_msm_ba_units_per_sm();
+size_t g1_msm_ba_point_bytes(size_t cnt_max);
+size_t g1_msm_ba_prefix_bytes(size_t cnt_max);
+void run_g1_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *buf_a, void *buf_b, void *prefix, size_t cnt_max, void *out);
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);

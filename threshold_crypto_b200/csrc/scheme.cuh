@@ -513,6 +513,8 @@ TCB_HD void task_g2_copy(size_t i, const u8 *in, u8 *out) {
 
 // ---- G1 tasks (always one item per thread)
 struct Jac1Store { Fp x, y, z; };
+TCB_HD void store_jac(Jac1Store &o, const Jac<Fp> &p) { o.x = p.x; o.y = p.y; o.z = p.z; }
+template <class F2> TCB_HD void store_jac(JacStore<F2> &o, const Jac<F2> &p) { p.x.store(o.x); p.y.store(o.y); p.z.store(o.z); }
 TCB_HD void task_g1_mul(size_t i, const u8 *sk, const u8 *pts_g1, u8 *out_g1) {   // a7 share / a9
     u32 k[8];
     load_scalar_le(k, sk + 32 * i);
@@ -595,6 +597,161 @@ TCB_HD void task_g1_msm_acc(size_t w, size_t m, size_t G, const Aff1Store *tab, 
     }
     out[w].x = acc.x; out[w].y = acc.y; out[w].z = acc.z;
 }
+// ---- batch-affine accumulation for the multi-scalar multiplication.
+// sum_s k_s P_s = sum_j 2^j S_j with S_j = sum_s (+-)T_s[d_{s,j}] a sum of AFFINE table entries.  All S_j are
+// formed by a pairwise tree over the shares; the additions of one tree level (all digit positions at once)
+// are AFFINE additions sharing ONE inversion (Montgomery's trick): 5M + 1S per addition instead of the
+// 7M + 4S of a mixed Jacobian addition, and the doublings happen only in the final Horner pass over the
+// per-position sums.  Working arrays (two ping-pong point buffers and the prefix products) live in a
+// scratch slab per unit.  Exceptional pairs (an operand at infinity, P + P, P + (-P)) are classified the same
+// way in both passes and contribute 1 to the running product.
+template <class F2> struct MsmG2 {
+    typedef F2 F;
+    typedef AffStore<F2> PS;
+    typedef Fp2c FS;
+    typedef Gls4Digits DG;
+    static constexpr int L = GLS4_L, TAB = 8;
+    TCB_HD static F fs_load(const FS &c) { return F2::load(c); }
+    TCB_HD static void fs_store(FS &c, const F &v) { v.store(c); }
+    TCB_HD static Aff<F> fetch(const PS *tab, const DG *dgs, size_t u, int j) { return g2_msm_fetch<F2>(tab, dgs, u, j); }
+};
+struct MsmG1 {
+    typedef Fp F;
+    typedef Aff1Store PS;
+    typedef Fp FS;
+    typedef Glv2Digits DG;
+    static constexpr int L = GLV2_L, TAB = 2;
+    TCB_HD static F fs_load(const FS &c) { return c; }
+    TCB_HD static void fs_store(FS &c, const F &v) { c = v; }
+    TCB_HD static Aff<F> fetch(const PS *tab, const DG *dgs, size_t u, int j) { return g1_msm_fetch(tab, dgs, u, j); }
+};
+template <class M> TCB_HD Aff<typename M::F> ps_load(const typename M::PS &e) {
+    Aff<typename M::F> t;
+    t.x = M::fs_load(e.x); t.y = M::fs_load(e.y);
+    t.inf = is_zero(t.x) && is_zero(t.y);           // (0, 0) is not on either curve: the infinity marker
+    return t;
+}
+template <class M> TCB_HD void ps_store(typename M::PS &e, const Aff<typename M::F> &t) {
+    typedef typename M::F F;
+    M::fs_store(e.x, t.inf ? FieldOne<F>::zero() : t.x);
+    M::fs_store(e.y, t.inf ? FieldOne<F>::zero() : t.y);
+}
+// classification of a pair; den = the element that enters the shared inversion
+enum { BA_REGULAR = 0, BA_TAKE_B = 1, BA_TAKE_A = 2, BA_DOUBLE = 3, BA_INF = 4 };
+template <class F> TCB_HD int ba_classify(const Aff<F> &a, const Aff<F> &b, F &den) {
+    den = FieldOne<F>::one();
+    if (a.inf) return BA_TAKE_B;
+    if (b.inf) return BA_TAKE_A;
+    if (eq(a.x, b.x)) {
+        if (eq(a.y, b.y)) { den = dbl(a.y); return BA_DOUBLE; }
+        return BA_INF;
+    }
+    den = b.x - a.x;
+    return BA_REGULAR;
+}
+template <class F> TCB_HD Aff<F> ba_finish(int kind, const Aff<F> &a, const Aff<F> &b, const F &dinv) {
+    if (kind == BA_TAKE_B) return b;
+    if (kind == BA_TAKE_A) return a;
+    Aff<F> r;
+    if (kind == BA_INF) { r.x = FieldOne<F>::zero(); r.y = FieldOne<F>::zero(); r.inf = true; return r; }
+    F lam;
+    if (kind == BA_DOUBLE) { F xx = sqr(a.x); lam = (dbl(xx) + xx) * dinv; }
+    else lam = (b.y - a.y) * dinv;
+    r.x = sqr(lam) - a.x - b.x;
+    r.y = lam * (a.x - r.x) - a.y;
+    r.inf = false;
+    return r;
+}
+// One tree level over all digit positions: in-points (j, i), i < n_in  ->  out-points (j, i), i < (n_in + 1) / 2.
+// `get(j, i)` reads an input point.  Pairs are enumerated position-major (k = j * pairs + i); both passes
+// fetch the operands of the NEXT pair before working on the current one (the kernels run 2-3 warps per
+// scheduler, so a global-memory round trip is not hidden by other warps: profiles/r5_*: 26-39 % long_sb).
+template <class M, class Get>
+TCB_HD void ba_level(size_t n_in, Get get, typename M::PS *out, size_t out_stride, typename M::FS *prefix) {
+    typedef typename M::F F;
+    const size_t pairs = n_in / 2, n_out = (n_in + 1) / 2;
+    const int NP = M::L + 1;
+    if (pairs) {
+        const size_t K = (size_t)NP * pairs;
+        F run = FieldOne<F>::one();
+        {
+            Aff<F> a = get(0, 0), b = get(0, 1);
+            for (size_t k = 0; k < K; k++) {
+                Aff<F> an = a, bn = b;
+                if (k + 1 < K) { size_t jn = (k + 1) / pairs, in = (k + 1) % pairs; an = get((int)jn, 2 * in); bn = get((int)jn, 2 * in + 1); }
+                F den;
+                ba_classify(a, b, den);
+                M::fs_store(prefix[k], run);          // product of the denominators BEFORE this pair
+                run = run * den;
+                a = an; b = bn;
+            }
+        }
+        F rinv = inv(run);
+        {
+            size_t jl = (K - 1) / pairs, il = (K - 1) % pairs;
+            Aff<F> a = get((int)jl, 2 * il), b = get((int)jl, 2 * il + 1);
+            F pf = M::fs_load(prefix[K - 1]);
+            for (size_t k = K; k-- > 0;) {
+                Aff<F> an = a, bn = b;
+                F pfn = pf;
+                if (k > 0) { size_t jn = (k - 1) / pairs, in = (k - 1) % pairs; an = get((int)jn, 2 * in); bn = get((int)jn, 2 * in + 1); pfn = M::fs_load(prefix[k - 1]); }
+                F den;
+                int kind = ba_classify(a, b, den);
+                F dinv = rinv * pf;
+                rinv = rinv * den;
+                ps_store<M>(out[(k / pairs) * out_stride + (k % pairs)], ba_finish(kind, a, b, dinv));
+                a = an; b = bn; pf = pfn;
+            }
+        }
+    }
+    if (n_in & 1)
+        for (int j = 0; j < NP; j++) ps_store<M>(out[(size_t)j * out_stride + n_out - 1], get(j, n_in - 1));
+}
+// scratch per unit: two point buffers of (L + 1) * ceil(cnt_max / 2) entries and (L + 1) * floor(cnt_max / 2) prefix products
+template <class M> TCB_HD size_t ba_points_per_unit(size_t cnt_max) { return (size_t)(M::L + 1) * ((cnt_max + 1) / 2); }
+template <class M> TCB_HD size_t ba_prefix_per_unit(size_t cnt_max) { size_t h = cnt_max / 2; return (size_t)(M::L + 1) * (h ? h : 1); }
+template <class M, class JS /* Jacobian store */>
+TCB_HD void task_msm_acc_ba(size_t w, size_t m, size_t G, const typename M::PS *tab, const typename M::DG *dgs,
+                            typename M::PS *buf_a, typename M::PS *buf_b, typename M::FS *prefix_all, size_t cnt_max, JS *out) {
+    typedef typename M::F F;
+    typedef typename M::PS PS;
+    size_t item = w / G, g = w % G;
+    size_t cnt = (m - g + G - 1) / G;
+    size_t base = item * m + g;
+    const size_t stride = (cnt_max + 1) / 2;
+    PS *A = buf_a + w * ba_points_per_unit<M>(cnt_max), *B = buf_b + w * ba_points_per_unit<M>(cnt_max);
+    typename M::FS *prefix = prefix_all + w * ba_prefix_per_unit<M>(cnt_max);
+    // level 0 reads the per-share tables through the recoded digits
+    size_t n = cnt;
+    ba_level<M>(n, [&](int j, size_t i) { return M::fetch(tab, dgs, base + i * G, j); }, A, stride, prefix);
+    n = (n + 1) / 2;
+    PS *cur = A, *nxt = B;
+    while (n > 1) {
+        const PS *src = cur;
+        ba_level<M>(n, [&](int j, size_t i) { return ps_load<M>(src[(size_t)j * stride + i]); }, nxt, stride, prefix);
+        n = (n + 1) / 2;
+        PS *t = cur; cur = nxt; nxt = t;
+    }
+    // Horner over the per-position sums
+    Jac<F> acc = jac_inf<F>();
+    Aff<F> sj = ps_load<M>(cur[(size_t)M::L * stride]);
+    for (int j = M::L; j >= 0; j--) {
+        Aff<F> sn = sj;
+        if (j > 0) sn = ps_load<M>(cur[(size_t)(j - 1) * stride]);
+        acc = jac_dbl(acc);
+        acc = jac_add_mixed(acc, sj);
+        sj = sn;
+    }
+    for (size_t s = 0; s < cnt; s++) {
+        size_t u = base + s * G;
+        if ((dgs[u].flags & 3u) != 1u) continue;     // the first mini-scalar was even: subtract P
+        Aff<F> t = ps_load<M>(tab[(size_t)M::TAB * u]);
+        t.y = -t.y;
+        acc = jac_add_mixed(acc, t);
+    }
+    store_jac(out[w], acc);
+}
+
 // a8: Commitment::evaluate (src/poly.rs:497-508): Horner, acc = acc * x + C_k.  The coefficient table is
 // decoded once (affine, Montgomery form; the point at infinity is stored as (0, 0), which is not on the
 // curve) so that "+ C_k" is a mixed addition; "acc * x" skips the leading zero bits of x (the indices

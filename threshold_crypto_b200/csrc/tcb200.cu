@@ -8,8 +8,10 @@
 //   k_hash_g2                   a2     SHA3 -> ChaCha20 -> G2::random -> exact cofactor (lane pairs)
 //   k_sign                      a4     sk * H(m)                                   (lane pairs)
 //   k_lagrange                  a5     lambda_i(0), one thread per (item, share)
-//   k_g2_msm_prep / k_g2_msm_acc / k_g2_sum   a6   shared-doubling multi-scalar multiplication (combine_signatures)
+//   k_g2_msm_prep / k_g2_msm_acc / k_g2_sum   a6   multi-scalar multiplication with shared doublings (combine_signatures)
 //   k_g1_mul / k_g1_msm_prep / k_g1_msm_acc / k_g1_sum / k_decrypt_finish   a7 (decrypt shares, decrypt)
+//   k_g*_msm_acc_ba (batch-affine tree: fewer multiplications, slower: memory latency) and k_g*_mul_store (one
+//   multiplication per share): alternatives kept for measurement (tcb_set_msm_algo)
 //   k_g1_decode / k_commit_eval a8     Commitment::evaluate (Horner)
 //   k_selftest_*, k_probe_*     measurement / self-test
 #include <cuda_runtime.h>
@@ -40,7 +42,7 @@ struct tcb_ctx {
     int engine = TCB_ENGINE_QUAD;
     int sm_count = 148;
     size_t msm_groups = 0;          // 0 = auto (pick_groups)
-    bool per_share_terms = false;   // measurement knob (env TCB200_PER_SHARE_TERMS=1): one scalar multiplication per share, no shared doublings
+    int msm_algo = 0;               // MSM_STRAUS (default) | MSM_BATCH_AFFINE | MSM_PER_SHARE (tcb_set_msm_algo; the others are measurement knobs)
 };
 
 #define CK(call)                                                                                        \
@@ -115,59 +117,68 @@ static int impl_sign(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *sk, cons
     if (n) RUN(run_sign(st, n, sk, msgs, off, h, out));
     return 0;
 }
-// ---- sum_s k_s P_s per item as a shared-doubling multi-scalar multiplication (scheme.cuh, *_msm_*).
-// Groups per item: G partial sums per item trade shared doublings (small G) against parallelism (large G);
-// pick the G that minimises  waves(n G) * (doublings + additions * ceil(m / G)).
-static size_t pick_groups(size_t n, size_t m, size_t units_per_wave, double dbl_cost, double add_cost) {
+// ---- sum_s k_s P_s per item as a multi-scalar multiplication (scheme.cuh, *_msm_*).
+// G partial sums ("groups") per item trade shared work (small G) against parallelism (large G); pick the G
+// that minimises  waves(n G) * (fixed + per_share * ceil(m / G)).
+static size_t pick_groups(size_t n, size_t m, size_t units_per_wave, double fixed_cost, double share_cost) {
     size_t best = 1;
     double best_cost = 1e300;
     for (size_t G = 1; G <= m; G++) {
         size_t per = (m + G - 1) / G;
         if (G > 1 && (m + G - 2) / (G - 1) == per) continue;          // same depth as G - 1 with more units
         double waves = (double)((n * G + units_per_wave - 1) / units_per_wave);
-        double cost = waves * (dbl_cost + add_cost * (double)per);
+        double cost = waves * (fixed_cost + share_cost * (double)per);
         if (cost < best_cost * 0.999) { best_cost = cost; best = G; }
     }
     return best;
 }
+enum { MSM_STRAUS = 0, MSM_BATCH_AFFINE = 1, MSM_PER_SHARE = 2, MSM_STRAUS_G2_THREAD = 3 };
 // out: G Jacobian partial sums per item in `part` (then run_g*_sum(n, G, part, ...))
-static int impl_msm_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
-    if (ctx->per_share_terms) {
+static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
+    const size_t term = g2 ? g2_term_bytes() : g1_term_bytes();
+    if (ctx->msm_algo == MSM_PER_SHARE) {
         G = m;
-        part = arena_alloc(ctx, d, n * m * g2_term_bytes());
+        part = arena_alloc(ctx, d, n * m * term);
         if (!part) return -1;
-        RUN(run_g2_mul_store(st, n * m, k, pts, part, status, m));
+        if (g2) RUN(run_g2_mul_store(st, n * m, k, pts, part, status, m));
+        else RUN(run_g1_mul_store(st, n * m, k, pts, part, status, m));
         return 0;
     }
-    static size_t per_sm = 0;
-    if (!per_sm) per_sm = g2_msm_units_per_sm();
-    G = ctx->msm_groups ? (ctx->msm_groups < m ? ctx->msm_groups : m) : pick_groups(n, m, per_sm * (size_t)ctx->sm_count, 4.8, 8.6);
-    void *tab = arena_alloc(ctx, d, n * m * g2_msm_tab_bytes());
-    void *dg = arena_alloc(ctx, d, n * m * g2_msm_dg_bytes());
-    part = arena_alloc(ctx, d, n * G * g2_term_bytes());
+    const bool ba = ctx->msm_algo == MSM_BATCH_AFFINE;
+    const bool g2_thread = g2 && ctx->msm_algo == MSM_STRAUS_G2_THREAD;
+    static size_t per_sm[5] = {0, 0, 0, 0, 0};
+    size_t &ps = per_sm[g2_thread ? 4 : (g2 ? 2 : 0) + (ba ? 1 : 0)];
+    if (!ps) ps = g2_thread ? g2_msm_thread_units_per_sm() : g2 ? (ba ? g2_msm_ba_units_per_sm() : g2_msm_units_per_sm()) : (ba ? g1_msm_ba_units_per_sm() : g1_msm_units_per_sm());
+    // relative costs in field multiplications: doubling 4.8 / 7, mixed addition 8.6 / 11, affine addition ~5.7 (+ one inversion per tree level)
+    double fixed = g2 ? (ba ? 4.8 + 8.6 + 6.0 : 4.8) : (ba ? 7.0 + 11.0 + 6.0 : 7.0);
+    double share = g2 ? (ba ? 5.2 : 8.6) : (ba ? 5.7 : 11.0);
+    G = ctx->msm_groups ? (ctx->msm_groups < m ? ctx->msm_groups : m) : pick_groups(n, m, ps * (size_t)ctx->sm_count, fixed, share);
+    void *tab = arena_alloc(ctx, d, n * m * (g2 ? g2_msm_tab_bytes() : g1_msm_tab_bytes()));
+    void *dg = arena_alloc(ctx, d, n * m * (g2 ? g2_msm_dg_bytes() : g1_msm_dg_bytes()));
+    part = arena_alloc(ctx, d, n * G * term);
     if (!tab || !dg || !part) return -1;
-    RUN(run_g2_msm_prep(st, n * m, k, pts, tab, dg, status, m));
-    RUN(run_g2_msm_acc(st, n * G, m, G, tab, dg, part));
+    if (g2) RUN(run_g2_msm_prep(st, n * m, k, pts, tab, dg, status, m));
+    else RUN(run_g1_msm_prep(st, n * m, k, pts, tab, dg, status, m));
+    if (!ba) {
+        if (g2_thread) RUN(run_g2_msm_acc_thread(st, n * G, m, G, tab, dg, part));
+        else if (g2) RUN(run_g2_msm_acc(st, n * G, m, G, tab, dg, part));
+        else RUN(run_g1_msm_acc(st, n * G, m, G, tab, dg, part));
+        return 0;
+    }
+    size_t cnt_max = (m + G - 1) / G;
+    size_t pb = g2 ? g2_msm_ba_point_bytes(cnt_max) : g1_msm_ba_point_bytes(cnt_max);
+    size_t fb = g2 ? g2_msm_ba_prefix_bytes(cnt_max) : g1_msm_ba_prefix_bytes(cnt_max);
+    void *buf_a = arena_alloc(ctx, d, n * G * pb), *buf_b = arena_alloc(ctx, d, n * G * pb), *prefix = arena_alloc(ctx, d, n * G * fb);
+    if (!buf_a || !buf_b || !prefix) return -1;
+    if (g2) RUN(run_g2_msm_acc_ba(st, n * G, m, G, tab, dg, buf_a, buf_b, prefix, cnt_max, part));
+    else RUN(run_g1_msm_acc_ba(st, n * G, m, G, tab, dg, buf_a, buf_b, prefix, cnt_max, part));
     return 0;
 }
+static int impl_msm_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
+    return impl_msm(ctx, d, st, true, n, m, k, pts, status, part, G);
+}
 static int impl_msm_g1(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
-    if (ctx->per_share_terms) {
-        G = m;
-        part = arena_alloc(ctx, d, n * m * g1_term_bytes());
-        if (!part) return -1;
-        RUN(run_g1_mul_store(st, n * m, k, pts, part, status, m));
-        return 0;
-    }
-    static size_t per_sm = 0;
-    if (!per_sm) per_sm = g1_msm_units_per_sm();
-    G = ctx->msm_groups ? (ctx->msm_groups < m ? ctx->msm_groups : m) : pick_groups(n, m, per_sm * (size_t)ctx->sm_count, 7.0, 11.0);
-    void *tab = arena_alloc(ctx, d, n * m * g1_msm_tab_bytes());
-    void *dg = arena_alloc(ctx, d, n * m * g1_msm_dg_bytes());
-    part = arena_alloc(ctx, d, n * G * g1_term_bytes());
-    if (!tab || !dg || !part) return -1;
-    RUN(run_g1_msm_prep(st, n * m, k, pts, tab, dg, status, m));
-    RUN(run_g1_msm_acc(st, n * G, m, G, tab, dg, part));
-    return 0;
+    return impl_msm(ctx, d, st, false, n, m, k, pts, status, part, G);
 }
 static int impl_combine_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     CK(cudaMemsetAsync(status, 0, n, st));
@@ -217,7 +228,7 @@ extern "C" int tcb_init(tcb_ctx **out, const int *device_ids, int n_devices) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return -3;   // no CPU fallback
     tcb_ctx *ctx = new tcb_ctx();
-    { const char *e = getenv("TCB200_PER_SHARE_TERMS"); ctx->per_share_terms = e && e[0] == '1'; }
+    { const char *e = getenv("TCB200_MSM_ALGO"); if (e && e[0] >= '0' && e[0] <= '3') ctx->msm_algo = e[0] - '0'; }
     Consts C;
     build_consts(C);
     if (n_devices <= 0 || !device_ids) {
@@ -264,6 +275,11 @@ extern "C" int tcb_set_engine(tcb_ctx *ctx, int engine) {
 extern "C" int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups) {
     if (!ctx) return -2;
     ctx->msm_groups = groups;
+    return 0;
+}
+extern "C" int tcb_set_msm_algo(tcb_ctx *ctx, int algo) {
+    if (!ctx || algo < 0 || algo > 3) return -2;
+    ctx->msm_algo = algo;
     return 0;
 }
 extern "C" uint64_t tcb_launch_count(const tcb_ctx *ctx) { return ctx ? ctx->launches : 0; }

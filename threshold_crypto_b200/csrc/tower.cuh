@@ -85,13 +85,13 @@ TCB_HDN Fp fp_pow(const Fp &a) {
     return acc;
 }
 TCB_HD Fp fp_inv_fermat(const Fp &a) { return fp_pow<ExpPm2>(a); }
-// Modular inverse by a branch-free binary GCD (Pornin, "Optimized binary GCD for modular
+// Modular inverse by a branch-free binary GCD, limb-by-limb reference version (Pornin, "Optimized binary GCD for modular
 // inversion", basic variant): 2*381 iterations of { if a odd: (swap if a < b); a -= b; u -= v }
 // a >>= 1; u /= 2 } with invariants a = u*y, b = v*y (mod p).  No multiplications: the work runs on
 // the ALU pipe and overlaps with other warps' IMAD.WIDE chains (a Fermat inverse is 570 Montgomery
 // multiplies, ~11% of a pairing check when replicated on the 4 lanes of a quad).
 // Input and output in Montgomery form: inv(aR) = a^-1 R^-1, then * R^3 * R^-1.  inv(0) = 0.
-TCB_HDN Fp fp_inv(const Fp &y) {
+TCB_HDN Fp fp_inv_basic(const Fp &y) {
     u32 a[12], b[12], u[12], v[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) { a[i] = y.l[i]; b[i] = FpParams::mod(i); u[i] = 0; v[i] = 0; }
@@ -137,6 +137,140 @@ TCB_HDN Fp fp_inv(const Fp &y) {
 #pragma unroll
         for (int i = 0; i < 11; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 31);
         u[11] = (u[11] >> 1) | (hi << 31);
+    }
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = v[i];
+    return r * CONSTS().r3;
+}
+// Modular inverse, production version: Pornin's OPTIMISED binary GCD (eprint 2020/972, Algorithm 2).  The 2x381
+// divsteps are done 30 at a time on 64-bit approximations (top 34 bits + low 30 bits of a and b), which yields
+// a 2x2 transition matrix (f0 g0; f1 g1) with |f| + |g| <= 2^30; the matrix is then applied to the full-length
+// (a, b) exactly and to (u, v) modulo p (a Montgomery-style division by 2^30).  26 rounds x (30 cheap steps + eight
+// 12-limb x 1-limb products) ~ 30 k instructions instead of the ~145 k of the limb-by-limb version below, which
+// is kept as an independent check (self-tests).  Same contract: Montgomery form in and out, inv(0) = 0.
+typedef int32_t s32;
+typedef int64_t s64;
+TCB_HD int clz32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return __builtin_clz(v);
+#endif
+}
+// t (14 limbs, two's complement) = f*x + g*y + k*m   for signed f, g with |f| + |g| <= 2^30, 0 <= k < 2^30
+TCB_HD void inv_lin(u32 *t, s32 f, const u32 *x, s32 g, const u32 *y, u32 k) {
+    s64 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        acc += (s64)f * (s64)(u64)x[i] + (s64)g * (s64)(u64)y[i] + (s64)((u64)k * (u64)FpParams::mod(i));
+        t[i] = (u32)acc;
+        acc >>= 32;
+    }
+    t[12] = (u32)acc;
+    t[13] = (u32)(acc >> 32);
+}
+TCB_HDN Fp fp_inv(const Fp &yin) {
+    const int K = 30, ROUNDS = 26;                 // 26 * 30 = 780 >= 2 * 381 - 1
+    u32 a[12], b[12], u[12], v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { a[i] = yin.l[i]; b[i] = FpParams::mod(i); u[i] = 0; v[i] = 0; }
+    u[0] = 1;
+    for (int rd = 0; rd < ROUNDS; rd++) {
+        // 64-bit window whose top bit is the top bit of (a | b), branch-free scan from the top limb
+        u32 a2 = a[11], a1 = a[10], a0 = a[9], b2 = b[11], b1 = b[10], b0 = b[9];
+#pragma unroll
+        for (int top = 11; top >= 3; top--) {
+            bool z = (a2 | b2) == 0;                // limb `top` empty in both: slide the window down one limb
+            a2 = z ? a1 : a2; a1 = z ? a0 : a1; a0 = z ? a[top - 3] : a0;
+            b2 = z ? b1 : b2; b1 = z ? b0 : b1; b0 = z ? b[top - 3] : b0;
+        }
+        bool small = (a2 | b2) == 0;                // a and b fit 64 bits: use them exactly
+        u64 ah, bh;
+        {
+            u32 m = a2 | b2;
+            int lz = m ? clz32(m) : 0;
+            u64 at = ((u64)a2 << 32) | a1, bt = ((u64)b2 << 32) | b1;
+            u64 a64 = lz ? ((at << lz) | (u64)(a0 >> (32 - lz))) : at;
+            u64 b64 = lz ? ((bt << lz) | (u64)(b0 >> (32 - lz))) : bt;
+            ah = (a64 & ~(u64)0x3fffffffu) | (a[0] & 0x3fffffffu);
+            bh = (b64 & ~(u64)0x3fffffffu) | (b[0] & 0x3fffffffu);
+            if (small) { ah = ((u64)a[1] << 32) | a[0]; bh = ((u64)b[1] << 32) | b[0]; }
+        }
+        s32 f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+        for (int i = 0; i < K; i++) {
+            bool odd = (ah & 1) != 0;
+            bool sw = odd && ah < bh;
+            u64 th = sw ? bh : ah; bh = sw ? ah : bh; ah = th;
+            s32 tf = sw ? f1 : f0; f1 = sw ? f0 : f1; f0 = tf;
+            s32 tg = sw ? g1 : g0; g1 = sw ? g0 : g1; g0 = tg;
+            ah -= odd ? bh : 0;
+            f0 -= odd ? f1 : 0;
+            g0 -= odd ? g1 : 0;
+            ah >>= 1;
+            f1 += f1; g1 += g1;
+        }
+        // (a, b) <- |(f0 a + g0 b, f1 a + g1 b)| / 2^30 (exact), the signs go into the matrix rows
+        u32 ta[14], tb[14];
+        inv_lin(ta, f0, a, g0, b, 0);
+        inv_lin(tb, f1, a, g1, b, 0);
+        bool na = (ta[13] >> 31) != 0, nb = (tb[13] >> 31) != 0;
+        {
+            u32 ca = na ? 1u : 0u, cb = nb ? 1u : 0u, ma = na ? 0xffffffffu : 0u, mb = nb ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int i = 0; i < 14; i++) {
+                u64 sa = (u64)(ta[i] ^ ma) + ca; ta[i] = (u32)sa; ca = (u32)(sa >> 32);
+                u64 sb = (u64)(tb[i] ^ mb) + cb; tb[i] = (u32)sb; cb = (u32)(sb >> 32);
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) { a[i] = (ta[i] >> 30) | (ta[i + 1] << 2); b[i] = (tb[i] >> 30) | (tb[i + 1] << 2); }
+        }
+        if (na) { f0 = -f0; g0 = -g0; }
+        if (nb) { f1 = -f1; g1 = -g1; }
+        // (u, v) <- (f0 u + g0 v, f1 u + g1 v) / 2^30 mod p: add k p with k = -t p^-1 mod 2^30, shift, one correction
+        u32 tu[14], tv[14];
+        {
+            u32 lu = (u32)f0 * u[0] + (u32)g0 * v[0], lv = (u32)f1 * u[0] + (u32)g1 * v[0];
+            inv_lin(tu, f0, u, g0, v, (lu * FpParams::INV) & 0x3fffffffu);
+            inv_lin(tv, f1, u, g1, v, (lv * FpParams::INV) & 0x3fffffffu);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) { u[i] = (tu[i] >> 30) | (tu[i + 1] << 2); v[i] = (tv[i] >> 30) | (tv[i + 1] << 2); }
+        // values are in (-p, 2p): top word (bits 384.. of the shifted value) tells the sign
+        s32 su = (s32)((tu[12] >> 30) | (tu[13] << 2)), sv = (s32)((tv[12] >> 30) | (tv[13] << 2));
+        {
+            // u: if negative add p; else subtract p if >= p
+            u32 t[12], bw;
+            sub_cc(t[0], u[0], FpParams::mod(0));
+#pragma unroll
+            for (int i = 1; i < 12; i++) subc_cc(t[i], u[i], FpParams::mod(i));
+            subc(bw, 0, 0);                                   // all-ones if u(low 384 bits) < p
+            bool neg = su < 0, ge = !neg && (su > 0 || bw == 0);
+            u32 am = neg ? 0xffffffffu : 0u;
+            u32 r[12];
+            add_cc(r[0], u[0], FpParams::mod(0) & am);
+#pragma unroll
+            for (int i = 1; i < 11; i++) addc_cc(r[i], u[i], FpParams::mod(i) & am);
+            addc(r[11], u[11], FpParams::mod(11) & am);
+#pragma unroll
+            for (int i = 0; i < 12; i++) u[i] = ge ? t[i] : r[i];
+        }
+        {
+            u32 t[12], bw;
+            sub_cc(t[0], v[0], FpParams::mod(0));
+#pragma unroll
+            for (int i = 1; i < 12; i++) subc_cc(t[i], v[i], FpParams::mod(i));
+            subc(bw, 0, 0);
+            bool neg = sv < 0, ge = !neg && (sv > 0 || bw == 0);
+            u32 am = neg ? 0xffffffffu : 0u;
+            u32 r[12];
+            add_cc(r[0], v[0], FpParams::mod(0) & am);
+#pragma unroll
+            for (int i = 1; i < 11; i++) addc_cc(r[i], v[i], FpParams::mod(i) & am);
+            addc(r[11], v[11], FpParams::mod(11) & am);
+#pragma unroll
+            for (int i = 0; i < 12; i++) v[i] = ge ? t[i] : r[i];
+        }
     }
     Fp r;
 #pragma unroll
