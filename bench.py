@@ -39,15 +39,19 @@ MSG_LEN = 32
 # Algorithmic 32x32->64 MACs per item of the product algorithms, counted by the instrumented
 # host emulation of the same code (tests/hostemu, see DESIGN.md "op counts").
 MACS_PER_VERIFY = None      # filled from profiles/op_counts.json if present
+MACS_PER_PAIRING = None
+MACS_PER_HASH = None
 MACS_PER_COMBINE = None
 
 
 def load_op_counts():
-    global MACS_PER_VERIFY, MACS_PER_COMBINE
+    global MACS_PER_VERIFY, MACS_PER_COMBINE, MACS_PER_PAIRING, MACS_PER_HASH
     p = os.path.join(ROOT, "profiles", "op_counts.json")
     if os.path.exists(p):
         d = json.load(open(p))
         MACS_PER_VERIFY = d.get("verify_macs_per_item")
+        MACS_PER_PAIRING = d.get("verify_g2_macs_per_item")
+        MACS_PER_HASH = d.get("hash_g2_macs_per_item")
         MACS_PER_COMBINE = d.get("combine_g2_t10_macs_per_item")
 
 
@@ -165,7 +169,9 @@ def run_reference(args):
         "impl": "reference", "metric": "bls_verifies_per_sec", "value": vps, "unit": "verifies/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (6x64 Montgomery, int)",
-        "data": "synthetic", "config": {"workload": "PublicKey::verify, bounded sample of the 2^16 batch", "sample_items_per_step": n},
+        "data": "synthetic", "config": {"workload": "PublicKey::verify (hash_g2 + pairing equality), BASELINE configs[1]", "items_per_gpu": N_VERIFY,
+                                        "msg_len": MSG_LEN, "corrupted": "i % 16 == 1", "sample_items_per_step": n,
+                                        "engine": "oracle/tc_oracle.c on the host cores (the reference crate needs Rust: not buildable here)"},
         "cpu_baseline": {"value": vps, "unit": "verifies/s", "cores": cores, "kind": "port",
                          "sample": f"{n} verifies/step x {args.steps} steps, oracle/tc_oracle.c with {cores} threads"},
         "combine": {"value": nc / dtc, "unit": "combines/s", "t": T_COMBINE, "sample": nc},
@@ -257,6 +263,29 @@ def run_gpu(args):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
     assert np.array_equal(d_ok.cpu().numpy(), expect)
+
+    # ---- per-kernel split of the step (rank 0): the two kernels behind tcb_verify_batch timed on their own entry points
+    # with the same inputs (k_hash_g2 -> H in HBM, then k_verify_g2_quad on (pk, H, g1, sig)); L2 flushed as above
+    kern_ms = None
+    if rank == 0:
+        d_h = torch.zeros(n * 192, dtype=torch.uint8, device=dev)
+
+        def step_hash():
+            E.dev_call("tcb_hash_g2_batch_dev", stream, ("size", n), d_msg.data_ptr(), d_off.data_ptr(), d_h.data_ptr())
+
+        def step_pair():
+            E.dev_call("tcb_verify_g2_batch_dev", stream, ("size", n), d_pk.data_ptr(), d_h.data_ptr(), 0, d_sig.data_ptr(), d_ok.data_ptr())
+        kern_ms = {}
+        for name, fn in (("k_hash_g2", step_hash), ("k_verify_g2_quad", step_pair)):
+            fn()
+            torch.cuda.synchronize()
+            kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for k in range(args.steps):
+                flush.fill_(k & 0xff)
+                kev[k][0].record(); fn(); kev[k][1].record()
+            torch.cuda.synchronize()
+            kern_ms[name] = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+        assert np.array_equal(d_ok.cpu().numpy(), expect), "split verify output wrong"
 
     # ---- e2e through the host-buffer C-ABI call
     for _ in range(2):
@@ -350,10 +379,23 @@ def run_gpu(args):
     if MACS_PER_VERIFY:
         ach = n * MACS_PER_VERIFY / (per_launch_ms * 1e-3)
         roof.update({"achieved": ach / 1e9, "frac": ach / imad_peak, "macs_per_item": MACS_PER_VERIFY,
-                     "frac_of_carry_chain_ceiling": ach / (fpmul_rate * 300)})
+                     "frac_of_carry_chain_ceiling": ach / (fpmul_rate * 300),
+                     "scope": "whole step = k_hash_g2 + k_verify_g2_quad (the per-kernel numbers are in roofline.kernels)"})
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        roof["traffic"] = json.load(open(tp)).get("k_verify_dram_bytes_per_launch")
+    traffic = json.load(open(tp)) if os.path.exists(tp) else {}
+    if kern_ms:
+        # the dominant kernel on its own: algorithmic MACs of one launch / its average launch duration (CUDA events above)
+        ks = {}
+        for name, macs in (("k_verify_g2_quad", MACS_PER_PAIRING), ("k_hash_g2", MACS_PER_HASH)):
+            ms = kern_ms[name]
+            k = {"ms_per_launch": ms, "share_of_step": ms / per_launch_ms, "dram_bytes_per_launch_ncu": traffic.get(name + "_dram_bytes_per_launch")}
+            if macs:
+                a = n * macs / (ms * 1e-3)
+                k.update({"macs_per_item": macs, "achieved": a / 1e9, "frac": a / imad_peak, "frac_of_carry_chain_ceiling": a / (fpmul_rate * 300)})
+            ks[name] = k
+        roof["kernels"] = ks
+        roof["dominant_kernel"] = "k_verify_g2_quad"
+        roof["traffic"] = traffic.get("k_verify_g2_quad_dram_bytes_per_launch")
 
     cpu = None
     if world == 1 and not args.no_cpu:
