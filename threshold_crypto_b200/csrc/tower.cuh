@@ -427,19 +427,21 @@ TCB_D Fp2S conj(const Fp2S &a) { Fp2S r; r.h = lane_role() ? -a.h : a.h; return 
 #define TCB_FP2S_CALL TCB_D
 #endif
 TCB_FP2S_CALL Fp2S operator*(const Fp2S &a, const Fp2S &b) {
-    Fp oa = partner(a.h), ob = partner(b.h);
     bool role = lane_role();
-    // role 0: a0*b0 + a1*(-b1) = h_a*h_b + o_a*(-o_b);  role 1: a0*b1 + a1*b0 = o_a*h_b + h_a*o_b
+    // role 0: a0*b0 + a1*(-b1) = h_a*h_b + o_a*(-o_b);  role 1: a0*b1 + a1*b0 = o_a*h_b + h_a*o_b.
+    // The c1 lane SENDS its half of b already negated: the negation runs on the lane's own data before the
+    // exchange instead of sitting between the shuffle and the multiply.
+    Fp oa = partner(a.h), ob = partner(fp_select(role, -b.h, b.h));
     Fp y1 = fp_select(role, ob, b.h);
-    Fp y2 = fp_select(role, b.h, -ob);
+    Fp y2 = fp_select(role, b.h, ob);
     Fp2S r; r.h = dot2(a.h, y1, oa, y2);
     return r;
 }
 TCB_FP2S_CALL Fp2S sqr(const Fp2S &a) {
     Fp o = partner(a.h);
     bool role = lane_role();
-    // role 0: (a0 + a1)(a0 - a1);  role 1: (2 a0) a1
-    Fp x = fp_select(role, dbl(o), a.h + o);
+    // role 0: (a0 + a1)(a0 - a1);  role 1: (a0 + a0) a1   (one addition, one subtraction, two selects)
+    Fp x = fp_select(role, o, a.h) + o;
     Fp y = fp_select(role, a.h, a.h - o);
     Fp2S r; r.h = x * y;
     return r;
