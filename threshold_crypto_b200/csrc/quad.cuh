@@ -170,7 +170,7 @@ __device__ __noinline__ Fp12Q fp12_cyclo_sqr(const Fp12Q &f) {
     }
     return r;
 }
-__device__ __noinline__ Fp12Q fp12_exp_by_x(const Fp12Q &f, u64 x) {
+__device__ __noinline__ Fp12Q fp12_exp_by_x_plain(const Fp12Q &f, u64 x) {
     Fp12Q acc = f;
     int top = 63;
     while (!((x >> top) & 1)) top--;
@@ -179,6 +179,98 @@ __device__ __noinline__ Fp12Q fp12_exp_by_x(const Fp12Q &f, u64 x) {
         acc = fp12_cyclo_sqr(acc);
         if ((x >> i) & 1) { TCB_PHASE(); acc = fp12_mul(acc, f); }
     }
+    return fp12_conj(acc);
+}
+// ---- Karabina's compressed squarings (eprint 2010/542) for the x-power runs.
+// In the cyclotomic subgroup (z0..z5 as in fp12_cyclo_sqr) the four coordinates (z2, z3, z4, z5) square among
+// themselves:  z4' = 3(z2^2 + xi z3^2) - 2 z4,  z3' = 3(z4^2 + xi z5^2) - 2 z3,  z2' = 3 xi (2 z4 z5) + 2 z2,
+// z5' = 3 (2 z2 z3) + 2 z5  — 3 product slots per lane instead of 5, a third of the exchanges and two thirds of
+// the linear work of the full Granger-Scott squaring (which executes 39 % of this kernel's instructions,
+// profiles/r2c_*).  f^|x| = prod over the set bits i of x of f^(2^i): the compressed chain is walked once, the
+// (six) needed powers are saved and decompressed together with ONE inversion:
+//     z1 = (xi z5^2 + 3 z4^2 - 2 z3) / (4 z2),    z0 = (2 z1^2 + z2 z5 - 3 z3 z4) xi + 1        (z2 != 0).
+// If some saved z2 is zero (f = 1 when both pairings are skipped; otherwise probability ~1/p^2) the whole power
+// falls back to the uncompressed loop, so every input is handled.
+struct CompQ { Fp2S a, b; };     // pair 0: (z4, z3); pair 1: (z2, z5)
+TCB_D CompQ q12_compress(const Fp12Q &f) {
+    bool p0 = quad_pair() == 0;
+    CompQ c;
+    c.a = select(p0, f.h.c1, f.h.c0);
+    c.b = f.h.c2;
+    return c;
+}
+__device__ __noinline__ CompQ comp_sqr(const CompQ &c) {
+    bool p0 = quad_pair() == 0;
+    Fp2S ob = xq(c.b);                                   // pair 0 gets z5, pair 1 gets z3
+    Fp2S sA = sqr(c.a), sB = sqr(c.b), sC = sqr(c.a + ob);   // pair 0: z4^2, z3^2, (z4+z5)^2 ; pair 1: z2^2, z5^2, (z2+z3)^2
+    Fp2S o_sA = xq(sA), o_sB = xq(sB), o_sC = xq(sC);
+    CompQ r;
+    Fp2S d;
+    if (p0) {
+        Fp2S t1 = o_sA + mul_xi(sB);                     // z2^2 + xi z3^2
+        Fp2S t2 = sA + mul_xi(o_sB);                     // z4^2 + xi z5^2
+        d = t1 - c.a; r.a = d + d + t1;                  // z4'
+        d = t2 - c.b; r.b = d + d + t2;                  // z3'
+    } else {
+        Fp2S u1 = mul_xi(o_sC - o_sA - sB);              // xi * 2 z4 z5
+        Fp2S u2 = sC - sA - o_sB;                        // 2 z2 z3
+        d = u1 + c.a; r.a = d + d + u1;                  // z2'
+        d = u2 + c.b; r.b = d + d + u2;                  // z5'
+    }
+    return r;
+}
+constexpr int COMP_MAX = 6;      // set bits of the exponent above bit 0 (6 for |x| and |x| >> 1)
+// product of the decompressed values c[0..n); false (quad-uniform) if a z2 is zero
+__device__ __noinline__ bool comp_decompress_product(const CompQ *c, int n, Fp12Q &prod) {
+    bool p0 = quad_pair() == 0;
+    Fp2S num[COMP_MAX], den[COMP_MAX], m[COMP_MAX], pre[COMP_MAX];
+    Fp2S run = Fp2S::one();
+    bool bad1 = false;
+    for (int k = 0; k < n; k++) {
+        Fp2S s = sqr(select(p0, c[k].a, c[k].b));        // pair 0: z4^2 ; pair 1: z5^2
+        m[k] = c[k].a * c[k].b;                          // pair 0: z4 z3 ; pair 1: z2 z5
+        Fp2S os = xq(s), ob = xq(c[k].b);                // pair 1 receives z4^2 and z3
+        num[k] = mul_xi(s) + (dbl(os) + os) - dbl(ob);   // pair 1: xi z5^2 + 3 z4^2 - 2 z3
+        den[k] = dbl(dbl(c[k].a));                       // pair 1: 4 z2
+        bool z = is_zero(den[k]);
+        bad1 = bad1 || (!p0 && z);
+        pre[k] = run;
+        run = run * den[k];
+    }
+    bool bad_o = xq_flag(bad1);                          // executed by all four lanes (no short-circuit around the shuffle)
+    if (bad1 | bad_o) return false;
+    Fp2S rinv = inv(run);
+    for (int k = n - 1; k >= 0; k--) {
+        Fp2S dinv = rinv * pre[k];
+        rinv = rinv * den[k];
+        Fp2S z1 = num[k] * dinv;                         // pair 1
+        Fp2S w = dbl(sqr(z1)) + m[k];                    // pair 1: 2 z1^2 + z2 z5
+        Fp2S ow = xq(w);
+        Fp2S z0 = mul_xi(ow - (dbl(m[k]) + m[k])) + Fp2S::one();   // pair 0: (2 z1^2 + z2 z5 - 3 z3 z4) xi + 1
+        Fp12Q dk;
+        dk.h.c0 = select(p0, z0, c[k].a);                // pair 0: (z0, z4, z3) ; pair 1: (z2, z1, z5)
+        dk.h.c1 = select(p0, c[k].a, z1);
+        dk.h.c2 = c[k].b;
+        prod = (k == n - 1) ? dk : fp12_mul(prod, dk);
+    }
+    return true;
+}
+__device__ __noinline__ Fp12Q fp12_exp_by_x(const Fp12Q &f, u64 x) {
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    CompQ saved[COMP_MAX];
+    int ns = 0;
+    CompQ c = q12_compress(f);
+    for (int i = 1; i <= top; i++) {
+        TCB_PHASE();
+        c = comp_sqr(c);
+        if (((x >> i) & 1) && ns < COMP_MAX) saved[ns++] = c;
+    }
+    int want = 0;
+    for (int i = 1; i <= top; i++) want += (int)((x >> i) & 1);
+    Fp12Q acc;
+    if (want != ns || ns == 0 || !comp_decompress_product(saved, ns, acc)) return fp12_exp_by_x_plain(f, x);
+    if (x & 1) acc = fp12_mul(acc, f);
     return fp12_conj(acc);
 }
 // same chain as final_exponentiation<F2> in tower.cuh
