@@ -199,24 +199,26 @@ TCB_D CompQ q12_compress(const Fp12Q &f) {
     c.b = f.h.c2;
     return c;
 }
+// Both pairs run ONE instruction stream (no pair-divergent branch): each pair multiplies by xi what only the other pair
+// needs in that form before sending it, the sums W and Q are common, and pair 1's extra steps are selected in.
 __device__ __noinline__ CompQ comp_sqr(const CompQ &c) {
     bool p0 = quad_pair() == 0;
     Fp2S ob = xq(c.b);                                   // pair 0 gets z5, pair 1 gets z3
     Fp2S sA = sqr(c.a), sB = sqr(c.b), sC = sqr(c.a + ob);   // pair 0: z4^2, z3^2, (z4+z5)^2 ; pair 1: z2^2, z5^2, (z2+z3)^2
-    Fp2S o_sA = xq(sA), o_sB = xq(sB), o_sC = xq(sC);
+    Fp2S xsB = mul_xi(sB);
+    Fp2S own = select(p0, xsB, sB);                      // kept:  pair 0: xi z3^2 ; pair 1: z5^2
+    Fp2S snd = select(p0, sB, xsB);                      // sent:  pair 0: z3^2    ; pair 1: xi z5^2
+    Fp2S o_sA = xq(sA), rcv = xq(snd), o_sC = xq(sC);
+    Fp2S W = o_sA + own;                                 // pair 0: z2^2 + xi z3^2 ; pair 1: z4^2 + z5^2
+    Fp2S Q = sA + rcv;                                   // pair 0: z4^2 + xi z5^2 ; pair 1: z2^2 + z3^2
+    Fp2S Ta = mul_xi(o_sC - W);                          // pair 1: xi * 2 z4 z5
+    Fp2S Tb = sC - Q;                                    // pair 1: 2 z2 z3
+    Fp2S Pa = select(p0, W, Ta), Pb = select(p0, Q, Tb);
     CompQ r;
-    Fp2S d;
-    if (p0) {
-        Fp2S t1 = o_sA + mul_xi(sB);                     // z2^2 + xi z3^2
-        Fp2S t2 = sA + mul_xi(o_sB);                     // z4^2 + xi z5^2
-        d = t1 - c.a; r.a = d + d + t1;                  // z4'
-        d = t2 - c.b; r.b = d + d + t2;                  // z3'
-    } else {
-        Fp2S u1 = mul_xi(o_sC - o_sA - sB);              // xi * 2 z4 z5
-        Fp2S u2 = sC - sA - o_sB;                        // 2 z2 z3
-        d = u1 + c.a; r.a = d + d + u1;                  // z2'
-        d = u2 + c.b; r.b = d + d + u2;                  // z5'
-    }
+    Fp2S da = select(p0, Pa - c.a, Pa + c.a);            // z4' = 3 Pa - 2 z4 | z2' = 3 Pa + 2 z2
+    Fp2S db = select(p0, Pb - c.b, Pb + c.b);            // z3' = 3 Pb - 2 z3 | z5' = 3 Pb + 2 z5
+    r.a = da + da + Pa;
+    r.b = db + db + Pb;
     return r;
 }
 constexpr int COMP_MAX = 6;      // set bits of the exponent above bit 0 (6 for |x| and |x| >> 1)
