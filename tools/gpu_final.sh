@@ -18,6 +18,7 @@ ncu -i gpurun_out/${T}_prof.ncu-rep --page details --csv > gpurun_out/${T}_verif
 ncu -i gpurun_out/${T}_prof.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_subset.py gpurun_out/${T}_verify_kernels_raw_subset.json
 for k in k_verify_g2_quad k_hash_g2; do
   ncu -i gpurun_out/${T}_prof.ncu-rep --page source --csv -k regex:$k 2>/dev/null | python profiles/agg_source.py gpurun_out/${T}_${k}_by_opcode.json > /dev/null 2>&1
+  ncu -i gpurun_out/${T}_prof.ncu-rep --page source --csv -k regex:$k 2>/dev/null | python profiles/agg_by_addr.py gpurun_out/${T}_${k}_by_addr.json 4096 > /dev/null 2>&1
 done
 rm -f gpurun_out/*.ncu-rep
 timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests -m gpu -x -q -k "msm or edges or golden" > gpurun_out/${T}_sanitizer_memcheck.txt 2>&1; tail -4 gpurun_out/${T}_sanitizer_memcheck.txt
