@@ -3,6 +3,7 @@
 // the hash kernel spent 61% of its stall samples on instruction fetch (profiles/r1d_*), as functions
 // k_hash_g2 runs 2x faster.  (The quad pairing kernel in k_pairing.cu prefers them inlined.)
 #define TCB_FP2S_NOINLINE 1
+#define TCB_FP_POW_CALL 1      // fixed-exponent powers (square roots) call one shared Fp multiply (tower.cuh)
 #include "kern.h"
 #include "scheme.cuh"
 using namespace tcb;

@@ -151,6 +151,15 @@ __global__ void k_selftest_quad(size_t n, u64 seed, unsigned long long *bad) {
         fp12_mul_by_014(t, l0, l1, l4);
         fp12_mul_by_014(qt, Fp2S::from_halves(l0.c0, l0.c1), Fp2S::from_halves(l1.c0, l1.c1), Fp2S::from_halves(l4.c0, l4.c1));
         errs += cmp_quad(qt, t);
+        // two lines at once (line product first) against two successive sparse multiplications of the scalar engine
+        Fp12T<Fp2> t2 = a; Fp12Q qt2 = qa;
+        fp12_mul_by_014(t2, l0, l1, l4);
+        fp12_mul_by_014(t2, l4, l0, l1);
+        LineS LA, LB;
+        LA.c0 = Fp2S::from_halves(l0.c0, l0.c1); LA.c1 = Fp2S::from_halves(l1.c0, l1.c1); LA.c4 = Fp2S::from_halves(l4.c0, l4.c1);
+        LB.c0 = LA.c4; LB.c1 = LA.c0; LB.c4 = LA.c1;
+        fp12_mul_by_two_lines(qt2, LA, LB);
+        errs += cmp_quad(qt2, t2);
     }
     if (((i >> 2) & 15) == 0) {
         errs += cmp_quad(fp12_inv(qa), fp12_inv(a));

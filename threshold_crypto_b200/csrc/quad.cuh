@@ -317,11 +317,57 @@ TCB_D LineS scale_line(const Line<Fp2S> &l, const Aff<Fp> &p) {
     r.c0 = l.c; r.c1 = mul_fp(l.b, p.x); r.c4 = mul_fp(l.a, p.y);
     return r;
 }
+// a * (y1 v + y2 v^2): 5 products
+TCB_D Fp6S fp6_mul_by_12(const Fp6S &a, const Fp2S &y1, const Fp2S &y2) {
+    Fp2S t1 = a.c1 * y1, t2 = a.c2 * y2;
+    Fp6S r;
+    r.c0 = mul_xi((a.c1 + a.c2) * (y1 + y2) - t1 - t2);
+    r.c1 = a.c0 * y1 + mul_xi(t2);
+    r.c2 = a.c0 * y2 + t1;
+    return r;
+}
+// f * A * B for two line elements (l0 + l1 v + l4 v w), both present on both pairs: the two lines are multiplied first
+// (6 products, 3 per pair, exchanged) into  L0 + L1 w,  L0 = (a0 b0 + xi a4 b4, a0 b1 + a1 b0, a1 b1),
+// L1 = (0, a0 b4 + a4 b0, a1 b4 + a4 b1), then each pair needs one full Fp6 product and one product by (0, y1, y2):
+// 14 product slots per lane instead of the 16 of two successive sparse multiplications.
+__device__ __noinline__ void fp12_mul_by_two_lines(Fp12Q &f, const LineS &A, const LineS &B) {
+    bool p0 = quad_pair() == 0;
+    // slot operands: pair 0: a0 b0, a1 b1, (a0+a1)(b0+b1) ; pair 1: a4 b4, (a0+a4)(b0+b4), (a1+a4)(b1+b4)
+    Fp2S x1 = select(p0, A.c0, A.c4), y1 = select(p0, B.c0, B.c4);
+    Fp2S x2 = select(p0, A.c1, A.c0 + A.c4), y2 = select(p0, B.c1, B.c0 + B.c4);
+    Fp2S x3 = select(p0, A.c0, A.c4) + A.c1, y3 = select(p0, B.c0, B.c4) + B.c1;
+    Fp6S q;
+    q.c0 = x1 * y1; q.c1 = x2 * y2; q.c2 = x3 * y3;
+    Fp6S o = xq(q);
+    Fp2S P00 = select(p0, q.c0, o.c0), P11 = select(p0, q.c1, o.c1), K01 = select(p0, q.c2, o.c2);
+    Fp2S P44 = select(p0, o.c0, q.c0), K04 = select(p0, o.c1, q.c1), K14 = select(p0, o.c2, q.c2);
+    Fp6S L0;
+    L0.c0 = P00 + mul_xi(P44);
+    L0.c1 = K01 - P00 - P11;
+    L0.c2 = P11;
+    Fp2S m1 = K04 - P00 - P44, m2 = K14 - P11 - P44;
+    Fp6S oth = xq(f.h);
+    Fp6S r1 = fp6_mul(f.h, L0);
+    Fp6S r2 = fp6_mul_by_12(oth, m1, m2);
+    f.h = r1 + sel6(p0, mul_v(r2), r2);
+}
 TCB_D void apply_lines(Fp12Q &f, const LineS &mine, bool act_mine, bool act_other) {
     bool p0 = quad_pair() == 0;
     LineS other = xq(mine);
     // line of pairing 0 first, then pairing 1 (same order on all four lanes)
     bool act0 = p0 ? act_mine : act_other, act1 = p0 ? act_other : act_mine;
+    // Measured (profiles/r2g_*): the line-product form needs 14 instead of 16 product slots per lane but the pairing kernel is
+    // SLOWER with it (79.5 vs 75.7 ms per 2^16): more live values around the Fp6 product at 255 registers.  Kept, self-tested,
+    // behind TCB_TWO_LINE_PRODUCT.
+#if defined(TCB_TWO_LINE_PRODUCT)
+    if (act0 && act1) {
+        LineS A, B;
+        A.c0 = select(p0, mine.c0, other.c0); A.c1 = select(p0, mine.c1, other.c1); A.c4 = select(p0, mine.c4, other.c4);
+        B.c0 = select(p0, other.c0, mine.c0); B.c1 = select(p0, other.c1, mine.c1); B.c4 = select(p0, other.c4, mine.c4);
+        fp12_mul_by_two_lines(f, A, B);
+        return;
+    }
+#endif
     if (act0) fp12_mul_by_014(f, select(p0, mine.c0, other.c0), select(p0, mine.c1, other.c1), select(p0, mine.c4, other.c4));
     if (act1) fp12_mul_by_014(f, select(p0, other.c0, mine.c0), select(p0, other.c1, mine.c1), select(p0, other.c4, mine.c4));
 }

@@ -67,20 +67,32 @@ TCB_EXP_TABLE(ExpRm2, 8, 0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x0
 TCB_HD Fp fp_one() { return CONSTS().r1; }
 
 // a^E for a compile-time exponent: fixed 4-bit windows (the exponents used here, (p+1)/4, (p-3)/4, p-2,
-// have ~190 one bits: 380 squarings + 95 window products + 14 for the table instead of 380 + 190)
+// have ~190 one bits: 380 squarings + 95 window products + 14 for the table instead of 380 + 190).
+// TCB_FP_POW_CALL (k_g2.cu): the five multiplies of the loop body are calls to one shared function; inlined they are
+// 38 KB of straight-line code against a 32 KB instruction cache (33-38 % instruction-fetch stalls in k_hash_g2).
+#if defined(TCB_FP_POW_CALL) && defined(__CUDACC__) && !defined(TCB_FP_NOINLINE)
+static __device__ __noinline__ Fp fp_pow_mul_call(const Fp &a, const Fp &b) { return mmul<FpParams>(a, b); }
+#endif
+TCB_HD Fp pw_mul(const Fp &a, const Fp &b) {
+#if defined(TCB_FP_POW_CALL) && defined(__CUDA_ARCH__) && !defined(TCB_FP_NOINLINE)
+    return fp_pow_mul_call(a, b);
+#else
+    return a * b;
+#endif
+}
 template <class E>
 TCB_HDN Fp fp_pow(const Fp &a) {
     Fp tab[16];
     tab[0] = fp_one();
     tab[1] = a;
-    for (int i = 2; i < 16; i++) tab[i] = tab[i - 1] * a;
+    for (int i = 2; i < 16; i++) tab[i] = pw_mul(tab[i - 1], a);
     int top = E::N * 8 - 1;                     // nibble index
     while (top > 0 && ((E::get(top >> 3) >> ((top & 7) * 4)) & 15u) == 0) top--;
     Fp acc = tab[(E::get(top >> 3) >> ((top & 7) * 4)) & 15u];
     for (int i = top - 1; i >= 0; i--) {
-        acc = sqr(sqr(sqr(sqr(acc))));
+        for (int k = 0; k < 4; k++) acc = pw_mul(acc, acc);
         u32 nib = (E::get(i >> 3) >> ((i & 7) * 4)) & 15u;
-        if (nib) acc = acc * tab[nib];
+        if (nib) acc = pw_mul(acc, tab[nib]);
     }
     return acc;
 }
