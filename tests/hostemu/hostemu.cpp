@@ -81,7 +81,9 @@ extern "C" int tcb_combine_g2_batch(tcb_ctx *, size_t n, size_t t, const u8 *x, 
     size_t m = t + 1;
     std::vector<u32> lam(n * m * 8);
     for (size_t i = 0; i < n; i++)
-        for (size_t k = 0; k < m; k++) lagrange_coeff(x + i * m * 32, m, k, &lam[8 * (i * m + k)], status[i]);
+        { std::vector<LagrangeND> nd(m);
+          for (size_t k = 0; k < m; k++) lagrange_num_den(x + i * m * 32, m, k, nd[k], status[i]);
+          lagrange_finish_item(nd.data(), m, &lam[8 * i * m]); }
     g2_msm(n, m, lam.data(), shares, out, status);
     return 0;
 }

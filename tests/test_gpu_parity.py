@@ -153,6 +153,23 @@ def test_msm_groupings_and_edges(gpu_engine, O):
         E.set_msm_algo(0)
 
 
+def test_two_pass_lagrange_large_batch(gpu_engine, O):
+    """Batches of >= 16 x SMs items take the two-pass Lagrange kernels (one shared inversion per item): interpolation
+    identity on every item and the oracle on a sample, incl. an item with a repeated index (by-value filter)."""
+    E = gpu_engine
+    O.set_threads(16)
+    n, t = 2500, 2
+    xs, sh, master = cases.make_combine_batch(O, n, t, 91, group=1, extra=5)
+    xs = xs.copy()
+    xs[32 * 3 * 7 + 32: 32 * 3 * 7 + 64] = xs[32 * 3 * 7: 32 * 3 * 7 + 32]        # item 7: x_1 := x_0
+    out, st = E.combine_g1_batch(n, t, xs, sh)
+    keep = np.arange(n) != 7
+    assert not st.any() and np.array_equal(out[keep], master[keep])
+    oo, _ = O.combine_g1_batch(16, t, xs[:16 * 3 * 32], sh[:16 * 3])
+    assert np.array_equal(out[:16], oo)
+    O.set_threads(1)
+
+
 def test_multi_device_ctx_matches_single(O):
     """A ctx over all visible devices shards contiguous slices and returns the same bytes."""
     import torch

@@ -14,6 +14,18 @@ __global__ void __launch_bounds__(128) k_lagrange(size_t n, size_t m, const u8 *
     lagrange_coeff(xs + item * m * 32, m, i, lam + 8 * t, st);
     if (st) status[item] = st;
 }
+__global__ void __launch_bounds__(128) k_lagrange_nd(size_t n, size_t m, const u8 *xs, LagrangeND *nd, u8 *status) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    size_t item = t / m, i = t % m;
+    u8 st = 0;
+    lagrange_num_den(xs + item * m * 32, m, i, nd[t], st);
+    if (st) status[item] = st;
+}
+__global__ void __launch_bounds__(128) k_lagrange_finish(size_t n, size_t m, LagrangeND *nd, u32 *lam) {
+    size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < n) lagrange_finish_item(nd + item * m, m, lam + 8 * item * m);
+}
 __global__ void __launch_bounds__(128) k_g1_mul(size_t n, const u8 *sk, const u8 *pts, u8 *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) task_g1_mul(i, sk, pts, out);
@@ -130,6 +142,12 @@ size_t g1_term_bytes() { return sizeof(Jac1Store); }
 size_t fp_bytes() { return sizeof(Fp); }
 void run_lagrange(cudaStream_t st, size_t n, size_t m, const u8 *xs, u32 *lam, u8 *status) {
     if (n * m) k_lagrange<<<grid1(n * m), 128, 0, st>>>(n, m, xs, lam, status);
+}
+size_t lagrange_nd_bytes() { return sizeof(LagrangeND); }
+void run_lagrange_two_pass(cudaStream_t st, size_t n, size_t m, const u8 *xs, void *nd, u32 *lam, u8 *status) {
+    if (!(n * m)) return;
+    k_lagrange_nd<<<grid1(n * m), 128, 0, st>>>(n, m, xs, (LagrangeND *)nd, status);
+    k_lagrange_finish<<<grid1(n), 128, 0, st>>>(n, m, (LagrangeND *)nd, lam);
 }
 void run_g1_mul(cudaStream_t st, size_t n, const u8 *sk, const u8 *pts, u8 *out) {
     if (n) k_g1_mul<<<grid1(n), 128, 0, st>>>(n, sk, pts, out);

@@ -41,6 +41,8 @@ void run_g2_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const 
 cudaError_t upload_consts_g1(const tcb::Consts &c);
 size_t g1_term_bytes();
 void run_lagrange(cudaStream_t st, size_t n, size_t m, const u8 *xs, u32 *lam, u8 *status);
+size_t lagrange_nd_bytes();
+void run_lagrange_two_pass(cudaStream_t st, size_t n, size_t m, const u8 *xs, void *nd, u32 *lam, u8 *status);   // 2 launches
 void run_g1_mul(cudaStream_t st, size_t n, const u8 *sk, const u8 *pts, u8 *out);
 void run_g1_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item);
 void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out);

@@ -7,7 +7,7 @@
 //   k_verify_g2_quad            a1/a3  pairing equality, one item per lane QUAD (quad.cuh)
 //   k_hash_g2                   a2     SHA3 -> ChaCha20 -> G2::random -> exact cofactor (lane pairs)
 //   k_sign                      a4     sk * H(m)                                   (lane pairs)
-//   k_lagrange                  a5     lambda_i(0), one thread per (item, share)
+//   k_lagrange | k_lagrange_nd + k_lagrange_finish   a5   lambda_i(0): one thread per (item, share), or two passes with one inversion per item
 //   k_g2_msm_prep / k_g2_msm_acc / k_g2_sum   a6   multi-scalar multiplication with shared doublings (combine_signatures)
 //   k_g1_mul / k_g1_msm_prep / k_g1_msm_acc / k_g1_sum / k_decrypt_finish   a7 (decrypt shares, decrypt)
 //   k_g*_msm_acc_ba (batch-affine tree: fewer multiplications, slower: memory latency) and k_g*_mul_store (one
@@ -180,6 +180,19 @@ static int impl_msm_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, siz
 static int impl_msm_g1(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
     return impl_msm(ctx, d, st, false, n, m, k, pts, status, part, G);
 }
+// Lagrange coefficients: with enough items to fill the GPU from one unit per ITEM, the two-pass form shares one inversion per item
+static int impl_lagrange(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t m, const u8 *x, u32 *lam, u8 *status) {
+    if (n >= (size_t)ctx->sm_count * 16) {
+        void *nd = arena_alloc(ctx, d, n * m * lagrange_nd_bytes());
+        if (!nd) return -1;
+        run_lagrange_two_pass(st, n, m, x, nd, lam, status);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    RUN(run_lagrange(st, n, m, x, lam, status));
+    return 0;
+}
 static int impl_combine_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     CK(cudaMemsetAsync(status, 0, n, st));
     if (n == 0) return 0;
@@ -187,7 +200,7 @@ static int impl_combine_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n,
     size_t m = t + 1;
     u32 *lam = (u32 *)arena_alloc(ctx, d, n * m * 32);
     if (!lam) return -1;
-    RUN(run_lagrange(st, n, m, x, lam, status));
+    if (impl_lagrange(ctx, d, st, n, m, x, lam, status)) return -1;
     void *part; size_t G;
     if (impl_msm_g2(ctx, d, st, n, m, lam, shares, status, part, G)) return -1;
     RUN(run_g2_sum(st, n, G, part, out));
@@ -206,7 +219,7 @@ static int impl_combine_g1(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n,
     size_t m = t + 1;
     u32 *lam = (u32 *)arena_alloc(ctx, d, n * m * 32);
     if (!lam) return -1;
-    RUN(run_lagrange(st, n, m, x, lam, status));
+    if (impl_lagrange(ctx, d, st, n, m, x, lam, status)) return -1;
     void *part; size_t G;
     if (impl_msm_g1(ctx, d, st, n, m, lam, shares, status, part, G)) return -1;
     if (mode == 0) RUN(run_g1_sum(st, n, G, part, out));
