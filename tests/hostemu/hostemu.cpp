@@ -159,6 +159,12 @@ extern "C" uint64_t tcb_emu_mac_count(int reset) { uint64_t v = g_mac_count; if 
 extern "C" int tcb_emu_inv_check(int n, uint64_t seed) {
     ensure();
     int bad = 0;
+    auto check = [&](const Fp &a, bool fermat) {
+        Fp x = fp_inv(a);                          // batched-divstep binary GCD (production)
+        if (x != fp_inv_basic(a)) bad++;           // limb-by-limb binary GCD
+        if (fermat && x != fp_inv_fermat(a)) bad++;
+        if (!a.is_zero() && (x * a) != fp_one()) bad++;
+    };
     for (int i = 0; i < n + 3; i++) {
         Fp a;
         for (;;) {
@@ -169,9 +175,18 @@ extern "C" int tcb_emu_inv_check(int n, uint64_t seed) {
         if (i == n) a = Fp::zero();
         if (i == n + 1) a = fp_one();
         if (i == n + 2) a = -fp_one();
-        Fp x = fp_inv(a), y = fp_inv_fermat(a);
-        if (x != y) bad++;
-        if (i < n && (x * a) != fp_one()) bad++;
+        check(a, i < 64 || i >= n);
+    }
+    // every bit length (the 64-bit approximations of the batched version slide with the top bit) and +-2^k
+    for (int bits = 1; bits <= 381; bits++) {
+        Fp a = Fp::zero();
+        for (int k = 0; k < 12; k++) { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; a.l[k] = (u32)(seed >> 32); }
+        int top = (bits - 1) / 32;
+        for (int k = top + 1; k < 12; k++) a.l[k] = 0;
+        a.l[top] &= 0xffffffffu >> (31 - ((bits - 1) % 32));
+        a.l[top] |= 1u << ((bits - 1) % 32);
+        if (limbs_lt_mod<FpParams>(a.l)) check(a, false);
+        if (bits <= 380) { Fp p2 = Fp::zero(); p2.l[(bits - 1) / 32] = 1u << ((bits - 1) % 32); check(p2, false); check(-p2, false); }
     }
     return bad;
 }

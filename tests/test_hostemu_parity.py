@@ -53,7 +53,8 @@ def test_hostemu_msm_groupings(emu, O):
 
 def test_binary_gcd_inverse_and_legendre_symbol(emu):
     """fp_inv (branch-free binary GCD) == Fermat inverse, fp_is_square (binary Jacobi) == Euler
-    criterion, on random elements and the edge values 0, 1, p-1 (host instantiation of tower.cuh)."""
+    criterion, on random elements, every bit length, +-2^k and the edge values 0, 1, p-1 (host instantiation of tower.cuh);
+    the production inverse (batched divsteps) is also compared with the limb-by-limb binary GCD."""
     import ctypes as C
     lib = emu.lib
     assert lib.tcb_emu_inv_check(500, C.c_uint64(99)) == 0
