@@ -191,6 +191,33 @@ extern "C" int tcb_emu_inv_check(int n, uint64_t seed) {
     return bad;
 }
 
+// test hook: Karabina compressed-squaring exponentiation (tower.cuh, the scalar statement of quad.cuh's device code) against the
+// Granger-Scott loop on n random elements of the cyclotomic subgroup, for |x| and |x| >> 1, plus f = 1 (fallback path)
+extern "C" int tcb_emu_karabina_check(int n, uint64_t seed) {
+    ensure();
+    int bad = 0;
+    for (int i = 0; i < n + 1; i++) {
+        Fp12T<Fp2> a;
+        Fp *c = (Fp *)&a;
+        for (int k = 0; k < 12; k++) {
+            for (;;) {
+                for (int w = 0; w < 12; w++) { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; c[k].l[w] = (u32)(seed >> 32); }
+                c[k].l[11] &= 0x1fffffffu;
+                if (limbs_lt_mod<FpParams>(c[k].l)) break;
+            }
+        }
+        Fp12T<Fp2> r = fp12_mul(fp12_conj(a), fp12_inv(a));     // easy part: a^((p^6 - 1)(p^2 + 1))
+        r = fp12_mul(fp12_frob(r, 2), r);
+        if (i == n) r = fp12_one<Fp2>();
+        const u64 x = TCB_BLS_X;
+        for (u64 e : {x, x >> 1}) {
+            Fp12T<Fp2> g = fp12_exp_by_x(r, e), k = fp12_exp_by_x_karabina(r, e);
+            const Fp *pg = (const Fp *)&g, *pk = (const Fp *)&k;
+            for (int w = 0; w < 12; w++) if (pg[w] != pk[w]) { bad++; break; }
+        }
+    }
+    return bad;
+}
 extern "C" int tcb_emu_issquare_check(int n, uint64_t seed) {
     ensure();
     int bad = 0, squares = 0;

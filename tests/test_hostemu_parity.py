@@ -62,5 +62,12 @@ def test_binary_gcd_inverse_and_legendre_symbol(emu):
     assert r // 100000 == 0 and 400 < r % 100000 < 620
 
 
+def test_karabina_compressed_squarings(emu):
+    """The compressed-squaring x-power (what quad.cuh runs on the device) equals the Granger-Scott loop on random elements of
+    the cyclotomic subgroup and on 1 (fallback when a saved z2 is zero)."""
+    import ctypes as C
+    assert emu.lib.tcb_emu_karabina_check(6, C.c_uint64(5)) == 0
+
+
 def test_hostemu_codecs(emu, O, golden):
     cases.check_codecs(emu, O, golden)

@@ -688,6 +688,65 @@ TCB_HDN Fp12T<F2> fp12_exp_by_x(const Fp12T<F2> &f, u64 x) {
     }
     return fp12_conj(acc);
 }
+// Karabina's compressed squarings, scalar-engine statement of what quad.cuh runs on the device (there spread over a lane
+// quad): (z2, z3, z4, z5) square among themselves; z1 = (xi z5^2 + 3 z4^2 - 2 z3) / (4 z2), z0 = (2 z1^2 + z2 z5 - 3 z3 z4) xi + 1.
+// Used by the host emulation to check the formulas and the fallback (tests/hostemu: tcb_emu_karabina_check).
+template <class F2> struct Comp4 { F2 z2, z3, z4, z5; };
+template <class F2>
+TCB_HD Comp4<F2> fp12_compress(const Fp12T<F2> &f) { Comp4<F2> c; c.z2 = f.c1.c0; c.z3 = f.c0.c2; c.z4 = f.c0.c1; c.z5 = f.c1.c2; return c; }
+template <class F2>
+TCB_HDN Comp4<F2> fp12_comp_sqr(const Comp4<F2> &c) {
+    F2 s2 = sqr(c.z2), s3 = sqr(c.z3), s4 = sqr(c.z4), s5 = sqr(c.z5);
+    F2 c23 = sqr(c.z2 + c.z3) - s2 - s3;      // 2 z2 z3
+    F2 c45 = sqr(c.z4 + c.z5) - s4 - s5;      // 2 z4 z5
+    F2 t1 = s2 + mul_xi(s3), t2 = s4 + mul_xi(s5), u1 = mul_xi(c45);
+    Comp4<F2> r;
+    F2 d;
+    d = t1 - c.z4; r.z4 = d + d + t1;
+    d = t2 - c.z3; r.z3 = d + d + t2;
+    d = u1 + c.z2; r.z2 = d + d + u1;
+    d = c23 + c.z5; r.z5 = d + d + c23;
+    return r;
+}
+// f^|x| then conjugate, through the compressed chain; falls back to the Granger-Scott loop when a saved z2 is zero
+template <class F2>
+TCB_HDN Fp12T<F2> fp12_exp_by_x_karabina(const Fp12T<F2> &f, u64 x) {
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    Comp4<F2> saved[64];
+    int ns = 0;
+    Comp4<F2> c = fp12_compress(f);
+    for (int i = 1; i <= top; i++) {
+        c = fp12_comp_sqr(c);
+        if ((x >> i) & 1) saved[ns++] = c;
+    }
+    if (ns == 0) return fp12_exp_by_x(f, x);
+    F2 pre[64], den[64];
+    F2 run = F2::one();
+    for (int k = 0; k < ns; k++) {
+        den[k] = dbl(dbl(saved[k].z2));
+        if (is_zero(den[k])) return fp12_exp_by_x(f, x);
+        pre[k] = run;
+        run = run * den[k];
+    }
+    F2 rinv = inv(run);
+    Fp12T<F2> acc = fp12_one<F2>();
+    for (int k = ns - 1; k >= 0; k--) {
+        const Comp4<F2> &s = saved[k];
+        F2 dinv = rinv * pre[k];
+        rinv = rinv * den[k];
+        F2 s4 = sqr(s.z4);
+        F2 z1 = (mul_xi(sqr(s.z5)) + (dbl(s4) + s4) - dbl(s.z3)) * dinv;
+        F2 m34 = s.z3 * s.z4;
+        F2 z0 = mul_xi(dbl(sqr(z1)) + s.z2 * s.z5 - (dbl(m34) + m34)) + F2::one();
+        Fp12T<F2> d;
+        d.c0.c0 = z0; d.c0.c1 = s.z4; d.c0.c2 = s.z3;
+        d.c1.c0 = s.z2; d.c1.c1 = z1; d.c1.c2 = s.z5;
+        acc = (k == ns - 1) ? d : fp12_mul(acc, d);
+    }
+    if (x & 1) acc = fp12_mul(acc, f);
+    return fp12_conj(acc);
+}
 // f^(3 (p^12 - 1)/r): easy part, then the hard part by the x-chain (same chain as EXTERNAL
 // pairing 0.16 final_exponentiation, with cyclotomic squarings).  Only == 1 is ever observed.
 template <class F2>
