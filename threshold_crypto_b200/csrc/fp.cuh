@@ -326,7 +326,7 @@ TCB_HD Fp operator-(const Fp &a) { return mneg<FpParams>(a); }
 // TCB_FP_NOINLINE (set per translation unit): the Fp multiply (and dot2) are real functions instead of ~390
 // (~590) inlined instructions per use.  The instruction caches are small (L1.5: 32 KB); a curve operation with
 // every multiply inlined is 50-100 KB of straight-line code and the G1 kernels spent 71 % of their stall
-// samples waiting for instructions (profiles/r2_*).  The pairing kernel keeps them inlined (measured).
+// samples waiting for instructions (profiles/r1s2_*).  The pairing kernel keeps them inlined (measured).
 #if defined(TCB_FP_NOINLINE) && defined(__CUDACC__)
 static __device__ __noinline__ Fp fp_mul_call(const Fp &a, const Fp &b) { return mmul<FpParams>(a, b); }
 static __device__ __noinline__ Fp fp_dot2_call(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return mdot2<FpParams>(a, b, c, d); }

@@ -186,7 +186,7 @@ __device__ __noinline__ Fp12Q fp12_exp_by_x_plain(const Fp12Q &f, u64 x) {
 // themselves:  z4' = 3(z2^2 + xi z3^2) - 2 z4,  z3' = 3(z4^2 + xi z5^2) - 2 z3,  z2' = 3 xi (2 z4 z5) + 2 z2,
 // z5' = 3 (2 z2 z3) + 2 z5  — 3 product slots per lane instead of 5, a third of the exchanges and two thirds of
 // the linear work of the full Granger-Scott squaring (which executes 39 % of this kernel's instructions,
-// profiles/r2c_*).  f^|x| = prod over the set bits i of x of f^(2^i): the compressed chain is walked once, the
+// profiles/r1s2c_*).  f^|x| = prod over the set bits i of x of f^(2^i): the compressed chain is walked once, the
 // (six) needed powers are saved and decompressed together with ONE inversion:
 //     z1 = (xi z5^2 + 3 z4^2 - 2 z3) / (4 z2),    z0 = (2 z1^2 + z2 z5 - 3 z3 z4) xi + 1        (z2 != 0).
 // If some saved z2 is zero (f = 1 when both pairings are skipped; otherwise probability ~1/p^2) the whole power
@@ -356,7 +356,7 @@ TCB_D void apply_lines(Fp12Q &f, const LineS &mine, bool act_mine, bool act_othe
     LineS other = xq(mine);
     // line of pairing 0 first, then pairing 1 (same order on all four lanes)
     bool act0 = p0 ? act_mine : act_other, act1 = p0 ? act_other : act_mine;
-    // Measured (profiles/r2g_*): the line-product form needs 14 instead of 16 product slots per lane but the pairing kernel is
+    // Measured (profiles/r1s2g_*): the line-product form needs 14 instead of 16 product slots per lane but the pairing kernel is
     // SLOWER with it (79.5 vs 75.7 ms per 2^16): more live values around the Fp6 product at 255 registers.  Kept, self-tested,
     // behind TCB_TWO_LINE_PRODUCT.
 #if defined(TCB_TWO_LINE_PRODUCT)

@@ -695,7 +695,7 @@ template <class F> TCB_HD Aff<F> ba_finish(int kind, const Aff<F> &a, const Aff<
 // One tree level over all digit positions: in-points (j, i), i < n_in  ->  out-points (j, i), i < (n_in + 1) / 2.
 // `get(j, i)` reads an input point.  Pairs are enumerated position-major (k = j * pairs + i); both passes
 // fetch the operands of the NEXT pair before working on the current one (the kernels run 2-3 warps per
-// scheduler, so a global-memory round trip is not hidden by other warps: profiles/r5_*: 26-39 % long_sb).
+// scheduler, so a global-memory round trip is not hidden by other warps: profiles/r1s2b_*: 26-39 % long_sb).
 template <class M, class Get>
 TCB_HD void ba_level(size_t n_in, Get get, typename M::PS *out, size_t out_stride, typename M::FS *prefix) {
     typedef typename M::F F;

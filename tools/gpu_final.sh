@@ -1,7 +1,7 @@
 #!/bin/bash
 # final evidence run of the round (one B200): parity suite, bench (both arms), other configs, launch list of the bench
 # command, ncu --set full of the two verify kernels, memcheck of the new kernels
-T=${1:-r2_final}
+T=${1:-r1s2_final}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest_gpu.txt
 tail -3 gpurun_out/${T}_pytest_gpu.txt
