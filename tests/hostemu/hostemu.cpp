@@ -69,7 +69,7 @@ static void g2_msm(size_t n, size_t m, const u32 *k, const u8 *pts, u8 *out, u8 
     for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, G, part.data(), out);
 }
 static void g1_msm(size_t n, size_t m, const u32 *k, const u8 *pts, Jac1Store *part, size_t G, u8 *status) {
-    std::vector<Aff1Store> tab(n * m * 2);
+    std::vector<Aff1Store> tab(n * m * 8);
     std::vector<Glv2Digits> dg(n * m);
     for (size_t u = 0; u < n * m; u++) task_g1_msm_prep(u, k, pts, tab.data(), dg.data(), status, m);
     if (g_algo == 1) msm_acc_ba<MsmG1>(n, m, G, tab.data(), dg.data(), part);

@@ -155,7 +155,7 @@ void run_g1_mul(cudaStream_t st, size_t n, const u8 *sk, const u8 *pts, u8 *out)
 void run_g1_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item) {
     if (units) k_g1_mul_store<<<grid1(units), 128, 0, st>>>(units, k, pts, (Jac1Store *)terms, status, per_item);
 }
-size_t g1_msm_tab_bytes() { return 2 * sizeof(Aff1Store); }
+size_t g1_msm_tab_bytes() { return 8 * sizeof(Aff1Store); }
 size_t g1_msm_dg_bytes() { return sizeof(Glv2Digits); }
 size_t g1_msm_units_per_sm() {
     int blocks = 0;

@@ -571,8 +571,8 @@ TCB_HD Aff<Fp> g1_sum(size_t i, size_t m, const Jac1Store *terms) {
     return jac_to_aff(acc);
 }
 // G1 version of the shared-doubling multi-scalar multiplication (decrypt, combine_g1, g1_lincomb): GLV2
-// recoding, table {P, P + P1} with P + P1 computed directly in affine coordinates (one inversion),
-// 130 shared doublings + 130 mixed additions per share.
+// recoding read two positions at a time (tower.cuh, glv2_table8: 8 affine entries per share, one inversion),
+// 130 shared doublings + 65 mixed additions per share.
 struct Aff1Store { Fp x, y; };
 TCB_HD void task_g1_msm_prep(size_t u, const u32 *k_limbs, const u8 *pts_g1, Aff1Store *tab, Glv2Digits *dgs, u8 *status, size_t per_item) {
     bool ok = true;
@@ -581,20 +581,20 @@ TCB_HD void task_g1_msm_prep(size_t u, const u32 *k_limbs, const u8 *pts_g1, Aff
     glv2_recode(k_limbs + 8 * u, dg);
     if (p.inf) dg.flags |= 2u;
     else {
-        Aff<Fp> t1 = glv2_t1_affine(p);
-        tab[2 * u].x = p.x; tab[2 * u].y = p.y;
-        tab[2 * u + 1].x = t1.x; tab[2 * u + 1].y = t1.y;
+        Aff<Fp> E[8];
+        glv2_table8(p, E);
+        for (int e = 0; e < 8; e++) { tab[8 * u + e].x = E[e].x; tab[8 * u + e].y = E[e].y; }
     }
     dgs[u] = dg;
     if (!ok) status[u / per_item] = 3;
 }
-TCB_HD Aff<Fp> g1_msm_fetch(const Aff1Store *tab, const Glv2Digits *dgs, size_t u, int j) {
-    u32 d = dgs[u].digit(j);
-    const Aff1Store &e = tab[2 * u + (d >> 1)];
+TCB_HD Aff<Fp> g1_msm_fetch(const Aff1Store *tab, const Glv2Digits *dgs, size_t u, int k) {
+    u32 nib = glv2_wdigit(dgs[u], k);
+    const Aff1Store &e = tab[8 * u + glv2_windex(nib)];
     Aff<Fp> t;
     t.x = e.x; t.y = e.y;
     t.inf = (dgs[u].flags & 2u) != 0;
-    if (d & 1) t.y = -t.y;
+    if (glv2_wneg(nib)) t.y = -t.y;
     return t;
 }
 TCB_HD void task_g1_msm_acc(size_t w, size_t m, size_t G, const Aff1Store *tab, const Glv2Digits *dgs, Jac1Store *out) {
@@ -602,8 +602,8 @@ TCB_HD void task_g1_msm_acc(size_t w, size_t m, size_t G, const Aff1Store *tab, 
     size_t cnt = (m - g + G - 1) / G;
     size_t base = item * m + g;
     Jac<Fp> acc = jac_inf<Fp>();
-    Aff<Fp> nxt = g1_msm_fetch(tab, dgs, base, GLV2_L);
-    int j = GLV2_L;
+    Aff<Fp> nxt = g1_msm_fetch(tab, dgs, base, GLV2_W);
+    int j = GLV2_W;
     size_t si = 0;
     for (;;) {
         Aff<Fp> cur = nxt;
@@ -613,7 +613,7 @@ TCB_HD void task_g1_msm_acc(size_t w, size_t m, size_t G, const Aff1Store *tab, 
         if (si2 == cnt) { si2 = 0; j2 = j - 1; }
         bool more = j2 >= 0;
         if (more) nxt = g1_msm_fetch(tab, dgs, base + si2 * G, j2);
-        if (row_start) acc = jac_dbl(acc);
+        if (row_start) acc = jac_dbl(jac_dbl(acc));
         acc = jac_add_mixed(acc, cur);
         if (!more) break;
         si = si2; j = j2;
@@ -622,7 +622,7 @@ TCB_HD void task_g1_msm_acc(size_t w, size_t m, size_t G, const Aff1Store *tab, 
         size_t u = base + s * G;
         if ((dgs[u].flags & 3u) != 1u) continue;
         Aff<Fp> t;
-        t.x = tab[2 * u].x; t.y = -tab[2 * u].y; t.inf = false;
+        t.x = tab[8 * u + 4].x; t.y = -tab[8 * u + 4].y; t.inf = false;      // entry 4 is P itself
         acc = jac_add_mixed(acc, t);
     }
     out[w].x = acc.x; out[w].y = acc.y; out[w].z = acc.z;
@@ -640,7 +640,7 @@ template <class F2> struct MsmG2 {
     typedef AffStore<F2> PS;
     typedef Fp2c FS;
     typedef Gls4Digits DG;
-    static constexpr int L = GLS4_L, TAB = 8;
+    static constexpr int L = GLS4_L, TAB = 8, P_ENTRY = 0, DBL = 1;    // positions 0..L, table entries, entry holding P, doublings per position
     TCB_HD static F fs_load(const FS &c) { return F2::load(c); }
     TCB_HD static void fs_store(FS &c, const F &v) { v.store(c); }
     TCB_HD static Aff<F> fetch(const PS *tab, const DG *dgs, size_t u, int j) { return g2_msm_fetch<F2>(tab, dgs, u, j); }
@@ -650,7 +650,7 @@ struct MsmG1 {
     typedef Aff1Store PS;
     typedef Fp FS;
     typedef Glv2Digits DG;
-    static constexpr int L = GLV2_L, TAB = 2;
+    static constexpr int L = GLV2_W, TAB = 8, P_ENTRY = 4, DBL = 2;
     TCB_HD static F fs_load(const FS &c) { return c; }
     TCB_HD static void fs_store(FS &c, const F &v) { c = v; }
     TCB_HD static Aff<F> fetch(const PS *tab, const DG *dgs, size_t u, int j) { return g1_msm_fetch(tab, dgs, u, j); }
@@ -768,14 +768,14 @@ TCB_HD void task_msm_acc_ba(size_t w, size_t m, size_t G, const typename M::PS *
     for (int j = M::L; j >= 0; j--) {
         Aff<F> sn = sj;
         if (j > 0) sn = ps_load<M>(cur[(size_t)(j - 1) * stride]);
-        acc = jac_dbl(acc);
+        for (int d = 0; d < M::DBL; d++) acc = jac_dbl(acc);
         acc = jac_add_mixed(acc, sj);
         sj = sn;
     }
     for (size_t s = 0; s < cnt; s++) {
         size_t u = base + s * G;
         if ((dgs[u].flags & 3u) != 1u) continue;     // the first mini-scalar was even: subtract P
-        Aff<F> t = ps_load<M>(tab[(size_t)M::TAB * u]);
+        Aff<F> t = ps_load<M>(tab[(size_t)M::TAB * u + M::P_ENTRY]);
         t.y = -t.y;
         acc = jac_add_mixed(acc, t);
     }

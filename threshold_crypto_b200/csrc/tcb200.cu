@@ -150,7 +150,8 @@ static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t 
     size_t &ps = per_sm[g2_thread ? 4 : (g2 ? 2 : 0) + (ba ? 1 : 0)];
     if (!ps) ps = g2_thread ? g2_msm_thread_units_per_sm() : g2 ? (ba ? g2_msm_ba_units_per_sm() : g2_msm_units_per_sm()) : (ba ? g1_msm_ba_units_per_sm() : g1_msm_units_per_sm());
     // relative costs in field multiplications: doubling 4.8 / 7, mixed addition 8.6 / 11, affine addition ~5.7 (+ one inversion per tree level)
-    double fixed = g2 ? (ba ? 4.8 + 8.6 + 6.0 : 4.8) : (ba ? 7.0 + 11.0 + 6.0 : 7.0);
+    // (G1 reads two digit positions per look-up: two doublings per position)
+    double fixed = g2 ? (ba ? 4.8 + 8.6 + 6.0 : 4.8) : (ba ? 14.0 + 11.0 + 6.0 : 14.0);
     double share = g2 ? (ba ? 5.2 : 8.6) : (ba ? 5.7 : 11.0);
     G = ctx->msm_groups ? (ctx->msm_groups < m ? ctx->msm_groups : m) : pick_groups(n, m, ps * (size_t)ctx->sm_count, fixed, share);
     void *tab = arena_alloc(ctx, d, n * m * (g2 ? g2_msm_tab_bytes() : g1_msm_tab_bytes()));

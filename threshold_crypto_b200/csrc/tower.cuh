@@ -1150,27 +1150,45 @@ TCB_HD void glv2_recode(const u32 *k_in, Glv2Digits &dg) {
         if (bit && neg && j < GLV2_L) { b0 += 1; if (b0 == 0) { b1 += 1; if (b1 == 0) b2 = 1; } }
     }
 }
-// P + P1 directly in affine coordinates (one inversion): lambda = -2y / ((beta - 1) x); x != 0 for a point of order r
-TCB_HD Aff<Fp> glv2_t1_affine(const Aff<Fp> &p) {
-    Fp bx = p.x * CONSTS().beta;
-    Fp lam = -dbl(p.y) * fp_inv(bx - p.x);
-    Aff<Fp> t;
-    t.x = sqr(lam) - p.x - bx;
-    t.y = lam * (p.x - t.x) - p.y;
-    t.inf = false;
-    return t;
+// Two digit positions per table look-up (width-2 window on the regular recoding): positions (2k, 2k+1) contribute
+//   s0 (P + i0 P1) + 2 s1 (P + i1 P1) = s1 [ (2 + sg) P + (2 i1 + sg i0) P1 ],   sg = s0 s1,
+// i.e. one of 8 points  E[4 n + 2 i1 + i0],  n = (sg == -1):  {3P + k P1, k = 0..3}  and  {P, P - P1, P + 2 P1, P + P1},
+// times the sign s1.  65 additions instead of 130 per scalar for a table of 8 affine points (1 doubling + 7 mixed additions
+// and one shared inversion to build).
+constexpr int GLV2_W = 64;   // window positions 0..GLV2_W
+TCB_HD u32 glv2_wdigit(const Glv2Digits &dg, int k) { return (dg.w[k >> 3] >> ((k & 7) * 4)) & 15u; }   // s0 | i0 << 1 | s1 << 2 | i1 << 3
+TCB_HD u32 glv2_windex(u32 nib) { return ((((nib ^ (nib >> 2)) & 1u)) << 2) | ((nib >> 2) & 2u) | ((nib >> 1) & 1u); }
+TCB_HD bool glv2_wneg(u32 nib) { return (nib & 4u) != 0; }
+TCB_HD void glv2_table8(const Aff<Fp> &p, Aff<Fp> *E) {
+    Aff<Fp> P1, nP1;
+    P1.x = p.x * CONSTS().beta; P1.y = -p.y; P1.inf = false;     // P1 = -phi(P) = [X^2] P
+    nP1 = P1; nP1.y = p.y;
+    Jac<Fp> J[7];
+    Jac<Fp> pj = jac_from_aff(p);
+    J[0] = jac_add_mixed(jac_dbl(pj), p);       // 3P
+    J[1] = jac_add_mixed(J[0], P1);             // 3P + P1
+    J[2] = jac_add_mixed(J[1], P1);             // 3P + 2 P1
+    J[3] = jac_add_mixed(J[2], P1);             // 3P + 3 P1
+    J[4] = jac_add_mixed(pj, nP1);              // P - P1
+    J[6] = jac_add_mixed(pj, P1);               // P + P1
+    J[5] = jac_add_mixed(J[6], P1);             // P + 2 P1
+    Aff<Fp> A[7];
+    jac_batch_to_aff<Fp, 7>(J, A);
+    E[0] = A[0]; E[1] = A[1]; E[2] = A[2]; E[3] = A[3];
+    E[4] = p; E[5] = A[4]; E[6] = A[5]; E[7] = A[6];
 }
 TCB_HDN Jac<Fp> jac_mul_glv2(const Aff<Fp> &p, const u32 *k_in) {
     if (p.inf) return jac_inf<Fp>();
     Glv2Digits dg;
     glv2_recode(k_in, dg);
-    Aff<Fp> T1 = glv2_t1_affine(p);
+    Aff<Fp> E[8];
+    glv2_table8(p, E);
     Jac<Fp> acc = jac_inf<Fp>();
-    for (int j = GLV2_L; j >= 0; j--) {
-        acc = jac_dbl(acc);
-        u32 d = dg.digit(j);
-        Aff<Fp> t = (d & 2) ? T1 : p;
-        if (d & 1) t.y = -t.y;
+    for (int k = GLV2_W; k >= 0; k--) {
+        acc = jac_dbl(jac_dbl(acc));
+        u32 nib = glv2_wdigit(dg, k);
+        Aff<Fp> t = E[glv2_windex(nib)];
+        if (glv2_wneg(nib)) t.y = -t.y;
         acc = jac_add_mixed(acc, t);
     }
     if (dg.flags & 1) { Aff<Fp> np = p; np.y = -p.y; acc = jac_add_mixed(acc, np); }
