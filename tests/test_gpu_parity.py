@@ -153,6 +153,27 @@ def test_msm_groupings_and_edges(gpu_engine, O):
         E.set_msm_algo(0)
 
 
+def test_scalar_mul_special_scalars_gpu(gpu_engine, O):
+    """The recodings' split points (multiples and neighbours of X^2 and X), 0, 1, r-1 and random scalars through the kernels."""
+    from conftest import R
+    E = gpu_engine
+    rng = np.random.default_rng(321)
+    X = 0xd201000000010000
+    X2 = X * X
+    ks = [0, 1, 2, 3, R - 1, R - 2, X2, X2 - 1, X2 + 1, 2 * X2, (1 << 128) - 1, 1 << 128, (1 << 129) + 1, X, X - 1, X + 1,
+          X ** 3 % R, (X ** 3 + 1) % R, (R - 1) // 2, (R + 1) // 2]
+    ks += [(a + b * X2) % R for a in (0, 1, (1 << 127) - 1, (1 << 128) - 1) for b in (1, (1 << 126) + 5, (1 << 127) - 1)]
+    ks += [int.from_bytes(rng.bytes(40), "little") % R for _ in range(32)]
+    n = len(ks)
+    sk = fr_bytes(ks)
+    O.set_threads(16)
+    base1 = O.g1_mul_gen_batch(fr_bytes([int.from_bytes(rng.bytes(40), "little") % R for _ in range(n)]))
+    assert np.array_equal(E.decrypt_share_batch(sk, base1), O.decrypt_share_batch(sk, base1))
+    base2 = O.sign_g2_batch(fr_bytes([int.from_bytes(rng.bytes(40), "little") % R for _ in range(n)]), np.tile(O.g2_generator(), (n, 1)))
+    assert np.array_equal(E.sign_g2_batch(sk, base2), O.sign_g2_batch(sk, base2))
+    O.set_threads(1)
+
+
 def test_two_pass_lagrange_large_batch(gpu_engine, O):
     """Batches of >= 16 x SMs items take the two-pass Lagrange kernels (one shared inversion per item): interpolation
     identity on every item and the oracle on a sample, incl. an item with a repeated index (by-value filter)."""

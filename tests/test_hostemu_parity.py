@@ -62,6 +62,25 @@ def test_binary_gcd_inverse_and_legendre_symbol(emu):
     assert r // 100000 == 0 and 400 < r % 100000 < 620
 
 
+def test_scalar_mul_special_scalars(emu, O):
+    """GLV2 (width-2 window) / GLS4 regular recodings on the scalars that stress them: 0, 1, r-1, multiples and neighbours of
+    X^2 and X (the split points), all-ones halves, plus random ones — against the oracle's double-and-add."""
+    from conftest import R
+    rng = np.random.default_rng(123)
+    X = 0xd201000000010000
+    X2 = X * X
+    ks = [0, 1, 2, 3, R - 1, R - 2, X2, X2 - 1, X2 + 1, 2 * X2, (1 << 128) - 1, 1 << 128, (1 << 129) + 1, X, X - 1, X + 1,
+          X ** 3 % R, (X ** 3 + 1) % R, (R - 1) // 2, (R + 1) // 2]
+    ks += [(a + b * X2) % R for a in (0, 1, (1 << 127) - 1, (1 << 128) - 1) for b in (1, (1 << 126) + 5, (1 << 127) - 1)]
+    ks += [int.from_bytes(rng.bytes(40), "little") % R for _ in range(24)]
+    n = len(ks)
+    sk = fr_bytes(ks)
+    base1 = O.g1_mul_gen_batch(fr_bytes([int.from_bytes(rng.bytes(40), "little") % R for _ in range(n)]))
+    assert np.array_equal(emu.decrypt_share_batch(sk, base1), O.decrypt_share_batch(sk, base1))
+    base2 = O.sign_g2_batch(fr_bytes([int.from_bytes(rng.bytes(40), "little") % R for _ in range(n)]), np.tile(O.g2_generator(), (n, 1)))
+    assert np.array_equal(emu.sign_g2_batch(sk, base2), O.sign_g2_batch(sk, base2))
+
+
 def test_karabina_compressed_squarings(emu):
     """The compressed-squaring x-power (what quad.cuh runs on the device) equals the Granger-Scott loop on random elements of
     the cyclotomic subgroup and on 1 (fallback when a saved z2 is zero)."""
