@@ -150,13 +150,22 @@ def run_reference(args):
     cores = host_threads()
     O.set_threads(cores)
     n = max(cores * 64, 256)        # bounded sample of the 2^16-verify workload per step (~6 ms of CPU per verify)
-    sk, pk, sig, msgs = cases.make_sig_batch(O, n, 2024, corrupt_every=16)
+    # the same synthetic shape as the GPU arm: 32-byte messages, every 16th signature (i % 16 == 5) replaced by its neighbour's
+    rng = np.random.default_rng(2024)
+    Rr = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    sk = np.frombuffer(b"".join((int.from_bytes(rng.bytes(40), "little") % Rr).to_bytes(32, "little") for _ in range(n)), np.uint8).copy()
+    msgs = [(0).to_bytes(4, "little") + i.to_bytes(8, "little") + b"\x5a" * (MSG_LEN - 12) for i in range(n)]
+    pk = O.g1_mul_gen_batch(sk)
+    sig = O.sign_batch(sk, msgs)
+    bad = np.arange(n) % 16 == 5
+    sig[bad] = np.roll(sig, 1, axis=0)[bad]
     for _ in range(max(args.warmup, 1)):
         O.verify_batch(pk, sig, msgs)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ok = O.verify_batch(pk, sig, msgs)
     dt = time.perf_counter() - t0
+    assert np.array_equal(ok.astype(bool), ~bad), "reference arm: unexpected verify results"
     vps = n * args.steps / dt
     # combines
     nc = max(cores, 8)
@@ -170,7 +179,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (6x64 Montgomery, int)",
         "data": "synthetic", "config": {"workload": "PublicKey::verify (hash_g2 + pairing equality), BASELINE configs[1]", "items_per_gpu": N_VERIFY,
-                                        "msg_len": MSG_LEN, "corrupted": "i % 16 == 1", "sample_items_per_step": n,
+                                        "msg_len": MSG_LEN, "corrupted": "i % 16 == 5", "sample_items_per_step": n,
                                         "engine": "oracle/tc_oracle.c on the host cores (the reference crate needs Rust: not buildable here)"},
         "cpu_baseline": {"value": vps, "unit": "verifies/s", "cores": cores, "kind": "port",
                          "sample": f"{n} verifies/step x {args.steps} steps, oracle/tc_oracle.c with {cores} threads"},
