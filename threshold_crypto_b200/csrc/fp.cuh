@@ -328,8 +328,8 @@ TCB_HD Fp operator-(const Fp &a) { return mneg<FpParams>(a); }
 // every multiply inlined is 50-100 KB of straight-line code and the G1 kernels spent 71 % of their stall
 // samples waiting for instructions (profiles/r1s2_*).  The pairing kernel keeps them inlined (measured).
 #if defined(TCB_FP_NOINLINE) && defined(__CUDACC__)
-static __device__ __noinline__ Fp fp_mul_call(const Fp &a, const Fp &b) { return mmul<FpParams>(a, b); }
-static __device__ __noinline__ Fp fp_dot2_call(const Fp &a, const Fp &b, const Fp &c, const Fp &d) { return mdot2<FpParams>(a, b, c, d); }
+static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { return mmul<FpParams>(a, b); }
+static __device__ __noinline__ Fp fp_dot2_call(Fp a, Fp b, Fp c, Fp d) { return mdot2<FpParams>(a, b, c, d); }
 #endif
 #if defined(TCB_FP_NOINLINE) && defined(__CUDA_ARCH__)
 TCB_HD Fp operator*(const Fp &a, const Fp &b) { return fp_mul_call(a, b); }

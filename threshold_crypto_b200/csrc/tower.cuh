@@ -438,7 +438,14 @@ TCB_D Fp2S conj(const Fp2S &a) { Fp2S r; r.h = lane_role() ? -a.h : a.h; return 
 #else
 #define TCB_FP2S_CALL TCB_D
 #endif
-TCB_FP2S_CALL Fp2S operator*(const Fp2S &a, const Fp2S &b) {
+// As real functions the operands are passed BY VALUE: the device ABI then hands the 12 limbs over in registers;
+// by reference they would have to be spilled to the local stack around every call.
+#if defined(TCB_FP2S_NOINLINE) && !defined(TCB_FP2S_BYREF)
+#define TCB_FP2S_ARG Fp2S
+#else
+#define TCB_FP2S_ARG const Fp2S &
+#endif
+TCB_FP2S_CALL Fp2S operator*(TCB_FP2S_ARG a, TCB_FP2S_ARG b) {
     bool role = lane_role();
     // role 0: a0*b0 + a1*(-b1) = h_a*h_b + o_a*(-o_b);  role 1: a0*b1 + a1*b0 = o_a*h_b + h_a*o_b.
     // The c1 lane SENDS its half of b already negated: the negation runs on the lane's own data before the
@@ -449,7 +456,7 @@ TCB_FP2S_CALL Fp2S operator*(const Fp2S &a, const Fp2S &b) {
     Fp2S r; r.h = dot2(a.h, y1, oa, y2);
     return r;
 }
-TCB_FP2S_CALL Fp2S sqr(const Fp2S &a) {
+TCB_FP2S_CALL Fp2S sqr(TCB_FP2S_ARG a) {
     Fp o = partner(a.h);
     bool role = lane_role();
     // role 0: (a0 + a1)(a0 - a1);  role 1: (a0 + a0) a1   (one addition, one subtraction, two selects)
