@@ -37,10 +37,10 @@ extern "C" {
 
 typedef struct tcb_ctx tcb_ctx;
 
-/* Engine variants for the G2 / pairing kernels (tcb_set_engine): */
-#define TCB_ENGINE_PAIR 0   /* one item per lane pair, Fp2 sliced across the pair */
-#define TCB_ENGINE_THREAD 1 /* one item per thread */
-#define TCB_ENGINE_QUAD 2   /* default: pairing checks on lane quads (register-resident Fp12), the rest on lane pairs */
+/* Engines of the pairing check (tcb_set_engine); both put one item on a quad of lanes and return the same booleans: */
+#define TCB_ENGINE_QUAD_REG 1  /* round-1 kernel: Miller loop + final exponentiation fused, Fp12 register-resident, exchanges by warp shuffles */
+#define TCB_ENGINE_QUAD_SMEM 2 /* default: Miller loop with its operands staged in shared memory (dot-product form, TMA bulk input
+                                  staging), f through HBM, then the final-exponentiation kernel */
 
 int tcb_init(tcb_ctx **ctx, const int *device_ids, int n_devices);
 void tcb_free(tcb_ctx *ctx);
@@ -141,6 +141,9 @@ int tcb_commitment_eval_batch_dev(tcb_ctx *, void *stream, size_t deg, const uin
 /* Runs the PTX Montgomery multiply, dot2, add, sub against the portable CIOS on n random
  * pairs on the device; returns the number of mismatches (0 = pass) or < 0 on CUDA failure. */
 int tcb_selftest_fp(tcb_ctx *, size_t n, uint64_t seed);
+/* Runs the Miller loop of both engines on the caller's n items (host buffers, c_g1 may be NULL) and returns the number of
+ * differing 32-bit words of the two results (0 = bit-identical) or < 0 on CUDA failure. */
+int tcb_selftest_miller(tcb_ctx *, size_t n, const uint8_t *a_g1, const uint8_t *b_g2, const uint8_t *c_g1, const uint8_t *d_g2);
 /* Integer-MAC roofline probe: dependent-free IMAD.WIDE.U32 chains on every SM; writes the
  * achieved 32x32->64 multiply-accumulates per second. */
 int tcb_probe_imad(tcb_ctx *, double *macs_per_sec);

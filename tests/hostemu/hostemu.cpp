@@ -218,6 +218,44 @@ extern "C" int tcb_emu_karabina_check(int n, uint64_t seed) {
     }
     return bad;
 }
+// K-term dot product with one interleaved reduction (fp.cuh, mont_dotk: the multiplier core of the shared-memory pairing
+// engine) against the sum of portable single products; operands include 0, 1, p - 1 and the non-canonical value p (what a
+// conditional negation of 0 produces).
+template <int K>
+static int dotk_check_one(uint64_t &seed, int mode) {
+    Fp x[K], y[K];
+    Fp ref = Fp::zero();
+    for (int k = 0; k < K; k++) {
+        for (int side = 0; side < 2; side++) {
+            Fp &v = side ? y[k] : x[k];
+            for (;;) {
+                for (int w = 0; w < 12; w++) { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; v.l[w] = (u32)(seed >> 32); }
+                v.l[11] &= 0x1fffffffu;
+                if (limbs_lt_mod<FpParams>(v.l)) break;
+            }
+            int sel = (mode + 3 * k + side) % 7;
+            if (mode && sel == 0) v = Fp::zero();
+            if (mode && sel == 1) { v = Fp::zero(); v.l[0] = 1; }
+            if (mode && sel == 2) { for (int w = 0; w < 12; w++) v.l[w] = FpParams::mod(w); v.l[0] -= 1; }
+            if (mode == 2) { for (int w = 0; w < 12; w++) v.l[w] = FpParams::mod(w); if (side) v.l[0] -= 1; }   // x = p (non-canonical), y = p - 1: the largest admissible sum
+        }
+        Fp xc = x[k];
+        if (!limbs_lt_mod<FpParams>(xc.l)) xc = Fp::zero();       // p == 0
+        ref = ref + mont_mul_portable<FpParams>(xc, y[k]);
+    }
+    Fp got = mont_dotk<FpParams, K>(x, y);
+    return (got != ref || !limbs_lt_mod<FpParams>(got.l)) ? 1 : 0;
+}
+extern "C" int tcb_emu_dotk_check(int n, uint64_t seed) {
+    ensure();
+    int bad = 0;
+    for (int i = 0; i < n; i++) {
+        int mode = i < 16 ? (i % 3) : 0;
+        bad += dotk_check_one<1>(seed, mode) + dotk_check_one<2>(seed, mode) + dotk_check_one<3>(seed, mode) + dotk_check_one<4>(seed, mode) +
+               dotk_check_one<6>(seed, mode) + dotk_check_one<8>(seed, mode);
+    }
+    return bad;
+}
 extern "C" int tcb_emu_issquare_check(int n, uint64_t seed) {
     ensure();
     int bad = 0, squares = 0;

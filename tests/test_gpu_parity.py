@@ -207,3 +207,57 @@ def test_multi_device_ctx_matches_single(O):
 
 def test_codecs(gpu_engine, O, golden):
     cases.check_codecs(gpu_engine, O, golden, n=40)
+
+
+def test_miller_engines_bit_identical(gpu_engine, O):
+    """The shared-memory Miller loop (quadsm.cuh: operands in shared memory, dot-product form, TMA input staging) against
+    the register engine's on the same items: f must be bit-identical.  70 items = two full blocks and a ragged tail; the
+    second call passes explicit C points, the third infinity operands."""
+    E = gpu_engine
+    n = 70
+    sk, pk, sig, msgs = cases.make_sig_batch(O, n, 91)
+    h = O.hash_g2_batch(msgs)
+    assert E.selftest_miller(pk, h, None, sig) == 0
+    g1 = np.tile(O.g1_generator(), (n, 1))
+    assert E.selftest_miller(pk, h, g1, sig) == 0
+    a = np.stack([cases.INF1, O.g1_generator(), cases.INF1, pk[0], pk[1]])
+    b = np.stack([O.g2_generator(), O.g2_generator(), cases.INF2, cases.INF2, h[1]])
+    c = np.stack([O.g1_generator(), cases.INF1, cases.INF1, pk[3], cases.INF1])
+    d = np.stack([cases.INF2, sig[0], O.g2_generator(), sig[3], sig[1]])
+    assert E.selftest_miller(a, b, c, d) == 0
+    assert np.array_equal(E.verify_g2_batch(a, b, c, d), O.verify_g2_batch(a, b, c, d))
+
+
+def test_both_pairing_engines_vs_oracle(gpu_engine, O):
+    """tcb_set_engine: the round-1 register kernel and the shared-memory engine return the oracle's booleans, also for
+    encodings >= p (ok = 0) and through device pointers that are NOT 16-byte aligned (plain-copy staging instead of TMA)."""
+    import torch
+    from threshold_crypto_b200._lib import ENGINE_QUAD_REG, ENGINE_QUAD_SMEM
+    E = gpu_engine
+    n = 45
+    sk, pk, sig, msgs = cases.make_sig_batch(O, n, 92, corrupt_every=3)
+    h = O.hash_g2_batch(msgs)
+    pk = pk.copy()
+    pk[7, :48] = 0xff                      # x >= p: invalid encoding -> false
+    exp = O.verify_g2_batch(pk, h, None, sig)
+    assert exp[7] == 0 and 0 < exp.sum() < n
+    try:
+        for eng in (ENGINE_QUAD_REG, ENGINE_QUAD_SMEM):
+            E.set_engine(eng)
+            assert np.array_equal(E.verify_g2_batch(pk, h, None, sig), exp)
+            assert np.array_equal(E.verify_batch(pk, sig, msgs), exp)
+        dev = torch.device("cuda", 0)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def off1(arr):
+            t = torch.zeros(arr.size + 17, dtype=torch.uint8, device=dev)
+            t[1:1 + arr.size] = torch.from_numpy(arr.reshape(-1)).to(dev)
+            return t[1:1 + arr.size]
+        d_pk, d_h, d_sig = off1(pk), off1(h), off1(sig)
+        assert d_pk.data_ptr() % 16 == 1
+        d_ok = torch.zeros(n, dtype=torch.uint8, device=dev)
+        E.dev_call("tcb_verify_g2_batch_dev", st, ("size", n), d_pk.data_ptr(), d_h.data_ptr(), 0, d_sig.data_ptr(), d_ok.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_ok.cpu().numpy(), exp)
+    finally:
+        E.set_engine(ENGINE_QUAD_SMEM)

@@ -90,3 +90,11 @@ def test_karabina_compressed_squarings(emu):
 
 def test_hostemu_codecs(emu, O, golden):
     cases.check_codecs(emu, O, golden)
+
+
+def test_dot_product_core(emu):
+    """mont_dotk (fp.cuh): K-term dot product with one interleaved Montgomery reduction, the multiplier core of the
+    shared-memory pairing engine, for K = 1, 2, 3, 4, 6, 8 against sums of portable products (incl. 0, 1, p - 1 and the
+    non-canonical operand p)."""
+    import ctypes as C
+    assert emu.lib.tcb_emu_dotk_check(300, C.c_uint64(17)) == 0

@@ -15,8 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TCB200_LIB selects an experiment build of the SAME CUDA library (e.g. another launch-bounds variant)
 DEFAULT_LIB = os.environ.get("TCB200_LIB") or os.path.join(_HERE, "csrc", "libtcb200.so")
 
-ENGINE_PAIR = 0
-ENGINE_THREAD = 1
+ENGINE_QUAD_REG = 1      # round-1 fused register-engine pairing kernel (self-test reference, A/B measurement)
+ENGINE_QUAD_SMEM = 2     # default: shared-memory Miller loop + final-exponentiation kernel
 
 
 class TcbError(RuntimeError):
@@ -230,6 +230,14 @@ class Engine:
     # ---- self-test / probes (CUDA library only)
     def selftest_fp(self, n=1 << 16, seed=1):
         rc = self.lib.tcb_selftest_fp(self.ctx, C.c_size_t(n), C.c_uint64(seed))
+        if rc < 0:
+            self._ck(rc)
+        return rc
+
+    def selftest_miller(self, a_g1, b_g2, c_g1, d_g2):
+        """differing words between the Miller-loop values of the shared-memory and the register engine (0 = identical)"""
+        a, b, c, d = _u8(a_g1), _u8(b_g2), _u8(c_g1), _u8(d_g2)
+        rc = self.lib.tcb_selftest_miller(self.ctx, C.c_size_t(a.size // 96), _p(a), _p(b), _p(c), _p(d))
         if rc < 0:
             self._ck(rc)
         return rc

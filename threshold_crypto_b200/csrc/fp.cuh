@@ -251,6 +251,103 @@ TCB_HD Mont<P> mont_mul_impl(const Mont<P> &a, const Mont<P> &b, const Mont<P> &
     return r;
 }
 
+// ---- K-term dot product  sum_k x_k * y_k * R^-1 mod p  with ONE interleaved Montgomery reduction (K <= 8 for BLS12-381:
+// the running value stays below (K + 1) p < 2^384).  The x operands are register-resident (K x N limbs); the y operands are
+// consumed four limbs at a time (one 128-bit vector per operand and chunk), so that a caller can stream them from shared
+// memory with 128-bit loads while the rows of the previous chunk are still being issued.  `dot_rows4` is one chunk (four
+// CIOS rows: the even/odd accumulator roles are back where they started), `dot_finish` merges the two accumulator arrays and
+// brings the result from [0, (K + 1) p) to the canonical range.
+template <class P, int K>
+TCB_HD void dot_row(u32 *even, u32 *odd, const u32 (*x)[P::N], const u32 *b) {
+    constexpr int N = P::N;
+    add_cc(even[0], even[0], odd[1]);
+    madc_n_rshift<N>(odd, x[0] + 1, b[0]);
+    cmad_n<N>(even, x[0], b[0]);
+    addc(odd[N - 1], odd[N - 1], 0);
+#pragma unroll
+    for (int k = 1; k < K; k++) {
+        cmad_n<N>(odd, x[k] + 1, b[k]);
+        cmad_n<N>(even, x[k], b[k]);
+        addc(odd[N - 1], odd[N - 1], 0);
+    }
+    u32 mi = even[0] * P::INV;
+    cmad_mod<P, 1>(odd, mi);
+    cmad_mod<P, 0>(even, mi);
+    addc(odd[N - 1], odd[N - 1], 0);
+}
+// y4[k][0..3]: limbs 4c .. 4c+3 of y_k
+template <class P, int K>
+TCB_HD void dot_rows4(u32 *even, u32 *odd, const u32 (*x)[P::N], const u32 (*y4)[4]) {
+    u32 b[K];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int k = 0; k < K; k++) b[k] = y4[k][r];
+        if (r & 1) dot_row<P, K>(odd, even, x, b);
+        else dot_row<P, K>(even, odd, x, b);
+    }
+}
+// k * mod as compile-time limbs (k a power of two <= 4: a shift)
+template <class P, int SH>
+struct ModShl {
+    TCB_HD static constexpr u32 limb(int i) {
+        return SH == 0 ? P::mod(i) : ((P::mod(i) << SH) | (i ? (P::mod(i - 1) >> (32 - SH)) : 0u));
+    }
+};
+template <class P, int SH>
+TCB_HD void cond_sub_shl(u32 *a) {          // a -= (mod << SH) if a >= (mod << SH)
+    constexpr int N = P::N;
+    u32 s[N], bw;
+    sub_cc(s[0], a[0], ModShl<P, SH>::limb(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) subc_cc(s[i], a[i], ModShl<P, SH>::limb(i));
+    subc(bw, 0, 0);
+    bool keep = bw != 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) a[i] = keep ? a[i] : s[i];
+}
+template <class P, int K>
+TCB_HD Mont<P> dot_finish(u32 *even, const u32 *odd) {
+    constexpr int N = P::N;
+    static_assert(K >= 1 && K <= 8, "dot product length");
+    add_cc(even[0], even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) addc_cc(even[i], even[i], odd[i + 1]);
+    addc(even[N - 1], even[N - 1], 0);
+    if (K + 1 > 4) cond_sub_shl<P, 2>(even);
+    if (K + 1 > 2) cond_sub_shl<P, 1>(even);
+    cond_sub_shl<P, 0>(even);
+    Mont<P> r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = even[i];
+    return r;
+}
+// reference use of the pieces (host emulation self-check and small device callers): all operands in registers
+template <class P, int K>
+TCB_HD Mont<P> mont_dotk(const Mont<P> *x, const Mont<P> *y) {
+    constexpr int N = P::N;
+#if !defined(__CUDA_ARCH__)
+    g_mac_count += (u64)(K + 1) * N * N + N;
+#endif
+    u32 xs[K][N], even[N], odd[N];
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+        for (int i = 0; i < N; i++) xs[k][i] = x[k].l[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) { even[i] = 0; odd[i] = 0; }
+#pragma unroll
+    for (int c = 0; c < N / 4; c++) {
+        u32 y4[K][4];
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) y4[k][r] = y[k].l[4 * c + r];
+        dot_rows4<P, K>(even, odd, xs, y4);
+    }
+    return dot_finish<P, K>(even, odd);
+}
+
 // Portable (no carry-flag tricks) CIOS used (a) by the host emulation as an independent
 // check of the PTX path and (b) on the device in the self-test kernel only.
 template <class P>

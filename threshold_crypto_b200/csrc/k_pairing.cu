@@ -18,6 +18,35 @@ __global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_verify_g2_quad(size_t n,
     bool res = pairing_eq_quad(a + 96 * i, b + 192 * i, c ? c + 96 * i : nullptr, d + 192 * i, enc_ok);
     if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok) ? 1 : 0;
 }
+// Final exponentiation + "== 1" of the Miller-loop values produced by k_miller_quad (k_miller.cu) or k_miller_quad_reg:
+// f of item i, lane l, coefficient k at fin[(4 i + l) * 3 + k]  (576 B per item through HBM/L2).
+__global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_final_exp_quad(size_t n, const Fp *fin, const u8 *enc_ok, u8 *ok) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    bool live = i < n;
+    if (!live) i = n - 1;
+    const Fp *p = fin + (i * 4 + (threadIdx.x & 3u)) * 3;
+    Fp12Q f;
+    f.h.c0.h = ldg_fp(p); f.h.c1.h = ldg_fp(p + 1); f.h.c2.h = ldg_fp(p + 2);
+    bool res = fp12_is_one(final_exponentiation(fp12_conj(f)));
+    if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok[i]) ? 1 : 0;
+}
+// the register engine's Miller loop alone, same output format (self-test reference for the shared-memory engine)
+__global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_miller_quad_reg(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, Fp *fout, u8 *enc_ok) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    bool live = i < n;
+    if (!live) i = n - 1;
+    bool enc;
+    Fp12Q f = miller_quad(a + 96 * i, b + 192 * i, c ? c + 96 * i : nullptr, d + 192 * i, enc);
+    if (live) {
+        Fp *o = fout + (i * 4 + (threadIdx.x & 3u)) * 3;
+        stg_fp(o, f.h.c0.h); stg_fp(o + 1, f.h.c1.h); stg_fp(o + 2, f.h.c2.h);
+        if ((threadIdx.x & 3) == 0) enc_ok[i] = enc ? 1 : 0;
+    }
+}
+__global__ void k_count_diff(size_t words, const u32 *x, const u32 *y, unsigned long long *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words && x[i] != y[i]) atomicAdd(bad, 1ULL);
+}
 // ---- self-test and roofline probes
 static __device__ __forceinline__ u64 splitmix(u64 &s) {
     u64 z = (s += 0x9e3779b97f4a7c15ULL);
@@ -175,12 +204,26 @@ namespace tcbk {
 cudaError_t upload_consts_pairing(const Consts &c) {
     // the pairing kernel keeps its small call frames in L1: no shared-memory carve-out
     cudaFuncSetAttribute(k_verify_g2_quad, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_final_exp_quad, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_miller_quad_reg, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     return cudaMemcpyToSymbol(d_consts, &c, sizeof c);
 }
 void run_verify_g2_quad(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
     if (!n) return;
     size_t threads = n * 4;
     k_verify_g2_quad<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, a, b, c, d, ok);
+}
+void run_final_exp_quad(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok) {
+    if (!n) return;
+    k_final_exp_quad<<<(unsigned)((n * 4 + 127) / 128), 128, 0, st>>>(n, (const Fp *)fbuf, enc_ok, ok);
+}
+void run_miller_quad_reg(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, void *fbuf, u8 *enc_ok) {
+    if (!n) return;
+    k_miller_quad_reg<<<(unsigned)((n * 4 + 127) / 128), 128, 0, st>>>(n, a, b, c, d, (Fp *)fbuf, enc_ok);
+}
+void run_count_diff(cudaStream_t st, size_t bytes, const void *x, const void *y, unsigned long long *bad) {
+    size_t words = bytes / 4;
+    if (words) k_count_diff<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(words, (const u32 *)x, (const u32 *)y, bad);
 }
 void run_selftest(cudaStream_t st, size_t n, u64 seed, unsigned long long *bad) {
     k_selftest_fp<<<(unsigned)(n / 128), 128, 0, st>>>(n, seed, bad);

@@ -2,7 +2,7 @@
 //
 // Why: with one item per thread (or per lane pair) an Fp12 accumulator is 144 (72) words per
 // thread, the Miller-loop state spills to local memory and the kernel becomes bound by L1/L2
-// latency at 2 warps/SMSP (profiles/r1_verify_pair.md).  Here an Fp12 value f = c0 + c1 w is
+// latency at 2 warps/SMSP (the first version of round 1).  Here an Fp12 value f = c0 + c1 w is
 // spread over a quad of lanes:
 //      lane = 2*j + e   (j = "pair", e = "role")   holds the Fp2-half e of every Fp2
 //      coefficient of c_j  ->  3 Fp = 36 registers per Fp12 value per lane.
@@ -371,9 +371,9 @@ TCB_D void apply_lines(Fp12Q &f, const LineS &mine, bool act_mine, bool act_othe
     if (act0) fp12_mul_by_014(f, select(p0, mine.c0, other.c0), select(p0, mine.c1, other.c1), select(p0, mine.c4, other.c4));
     if (act1) fp12_mul_by_014(f, select(p0, other.c0, mine.c0), select(p0, other.c1, mine.c1), select(p0, other.c4, mine.c4));
 }
-// e(a,b) == e(c,d), evaluated by one quad.  Every lane passes the pointers of the item; pair 0
-// loads (a, b), pair 1 loads (-c, d).
-__device__ __noinline__ bool pairing_eq_quad(const u8 *a_g1, const u8 *b_g2, const u8 *c_g1, const u8 *d_g2, bool &ok_enc) {
+// The two-pairing Miller loop of e(a,b) * e(-c,d) on one quad (before the final conjugation).  Every lane passes the
+// pointers of the item; pair 0 loads (a, b), pair 1 loads (-c, d).
+__device__ __noinline__ Fp12Q miller_quad(const u8 *a_g1, const u8 *b_g2, const u8 *c_g1, const u8 *d_g2, bool &ok_enc) {
     bool p0 = quad_pair() == 0;
     bool ok = true;
     Aff<Fp> p;
@@ -404,9 +404,26 @@ __device__ __noinline__ bool pairing_eq_quad(const u8 *a_g1, const u8 *b_g2, con
     TCB_PHASE();
     LineS l = scale_line(doubling_step(t), p);
     apply_lines(f, l, act, act_o);
-    f = fp12_conj(f);
+    return f;
+}
+// e(a,b) == e(c,d), evaluated by one quad (the round-1 register engine, kept for the self-test and for A/B measurements)
+__device__ __noinline__ bool pairing_eq_quad(const u8 *a_g1, const u8 *b_g2, const u8 *c_g1, const u8 *d_g2, bool &ok_enc) {
+    Fp12Q f = fp12_conj(miller_quad(a_g1, b_g2, c_g1, d_g2, ok_enc));
     TCB_PHASE();
     return fp12_is_one(final_exponentiation(f));
+}
+// an Fp in global memory as three 128-bit vectors (scratch buffers are 16-byte aligned)
+TCB_D Fp ldg_fp(const Fp *p) {
+    const uint4 *q = (const uint4 *)p;
+    uint4 a = q[0], b = q[1], c = q[2];
+    Fp r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
+    return r;
+}
+TCB_D void stg_fp(Fp *p, const Fp &v) {
+    uint4 *q = (uint4 *)p;
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]); q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]); q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
 }
 
 }  // namespace tcb

@@ -4,7 +4,9 @@
 // every entry point enqueues CUDA kernels or fails with an error code.
 //
 // Kernel inventory:
-//   k_verify_g2_quad            a1/a3  pairing equality, one item per lane QUAD (quad.cuh)
+//   k_miller_quad + k_final_exp_quad   a1/a3  pairing equality, one item per lane QUAD: Miller loop with its operands staged in
+//                               shared memory (quadsm.cuh), f through HBM, final exponentiation on the register engine (quad.cuh)
+//   k_verify_g2_quad            the round-1 fused register-engine kernel (TCB_ENGINE_QUAD_REG: self-test reference, A/B measurement)
 //   k_hash_g2                   a2     SHA3 -> ChaCha20 -> G2::random -> exact cofactor (lane pairs)
 //   k_sign                      a4     sk * H(m)                                   (lane pairs)
 //   k_lagrange | k_lagrange_nd + k_lagrange_finish   a5   lambda_i(0): one thread per (item, share), or two passes with one inversion per item
@@ -39,7 +41,7 @@ struct tcb_ctx {
     std::vector<DevState> devs;
     std::string err;
     uint64_t launches = 0;
-    int engine = TCB_ENGINE_QUAD;
+    int engine = TCB_ENGINE_QUAD_SMEM;
     int sm_count = 148;
     size_t msm_groups = 0;          // 0 = auto (pick_groups)
     int msm_algo = 0;               // MSM_STRAUS (default) | MSM_BATCH_AFFINE | MSM_PER_SHARE (tcb_set_msm_algo; the others are measurement knobs)
@@ -96,8 +98,15 @@ static void *arena_alloc(tcb_ctx *ctx, DevState &d, size_t bytes) {
     } while (0)
 
 // ----------------------------------------------------------------------------- device-side implementations
-static int impl_verify_g2(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
-    if (n) RUN(run_verify_g2_quad(st, n, a, b, c, d, ok));
+static int impl_verify_g2(tcb_ctx *ctx, DevState &dv, cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
+    if (!n) return 0;
+    if (ctx->engine == TCB_ENGINE_QUAD_REG) { RUN(run_verify_g2_quad(st, n, a, b, c, d, ok)); return 0; }
+    // Miller loop (shared-memory engine) -> f, 576 B per item in scratch -> final exponentiation and "== 1"
+    void *fbuf = arena_alloc(ctx, dv, n * miller_f_bytes());
+    u8 *enc = (u8 *)arena_alloc(ctx, dv, n);
+    if (!fbuf || !enc) return -1;
+    RUN(run_miller_quad(st, n, a, b, c, d, fbuf, enc));
+    RUN(run_final_exp_quad(st, n, fbuf, enc, ok));
     return 0;
 }
 static int impl_hash_g2(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
@@ -110,8 +119,7 @@ static int impl_verify(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, con
     u8 *h = (u8 *)arena_alloc(ctx, d, n * 192);
     if (!h) return -1;
     RUN(run_hash_g2(st, n, msgs, off, h));
-    RUN(run_verify_g2_quad(st, n, pk, h, nullptr, sig, ok));
-    return 0;
+    return impl_verify_g2(ctx, d, st, n, pk, h, nullptr, sig, ok);
 }
 static int impl_sign(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     if (n) RUN(run_sign(st, n, sk, msgs, off, h, out));
@@ -259,7 +267,8 @@ extern "C" int tcb_init(tcb_ctx **out, const int *device_ids, int n_devices) {
         if (d.dev < 0 || d.dev >= count) { delete ctx; return -4; }
         if (cudaSetDevice(d.dev) != cudaSuccess) { delete ctx; return -5; }
         if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -6; }
-        if (upload_consts_pairing(C) != cudaSuccess || upload_consts_g2(C) != cudaSuccess || upload_consts_g1(C) != cudaSuccess) { delete ctx; return -7; }
+        if (upload_consts_pairing(C) != cudaSuccess || upload_consts_miller(C) != cudaSuccess || upload_consts_g2(C) != cudaSuccess ||
+            upload_consts_g1(C) != cudaSuccess) { delete ctx; return -7; }
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->devs[0].dev) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -282,7 +291,7 @@ extern "C" void tcb_free(tcb_ctx *ctx) {
 }
 extern "C" const char *tcb_last_error(const tcb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" int tcb_set_engine(tcb_ctx *ctx, int engine) {
-    if (!ctx || engine != TCB_ENGINE_QUAD) return -2;   // the other engines are debug builds only
+    if (!ctx || (engine != TCB_ENGINE_QUAD_SMEM && engine != TCB_ENGINE_QUAD_REG)) return -2;
     ctx->engine = engine;
     return 0;
 }
@@ -308,7 +317,7 @@ extern "C" uint64_t tcb_launch_count(const tcb_ctx *ctx) { return ctx ? ctx->lau
 
 extern "C" int tcb_verify_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *dd, u8 *ok) {
     DEV_PROLOGUE
-    return impl_verify_g2(ctx, st, n, a, b, c, dd, ok);
+    return impl_verify_g2(ctx, d, st, n, a, b, c, dd, ok);
 }
 extern "C" int tcb_hash_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     DEV_PROLOGUE
@@ -409,7 +418,7 @@ extern "C" int tcb_verify_g2_batch(tcb_ctx *ctx, size_t n, const u8 *a, const u8
         u8 *dc = c ? up(ctx, d, c + 96 * s.lo, 96 * cnt) : nullptr, *ddv = up(ctx, d, dd + 192 * s.lo, 192 * cnt);
         u8 *dok = (u8 *)arena_alloc(ctx, d, cnt);
         if (!da || !db || (c && !dc) || !ddv || !dok) return -1;
-        if (impl_verify_g2(ctx, st, cnt, da, db, dc, ddv, dok)) return -1;
+        if (impl_verify_g2(ctx, d, st, cnt, da, db, dc, ddv, dok)) return -1;
         if (down(ctx, d, ok + s.lo, dok, cnt)) return -1;
     END_FOR_EACH_DEV
     return sync_all(ctx);
@@ -637,6 +646,32 @@ extern "C" int tcb_selftest_fp(tcb_ctx *ctx, size_t n, uint64_t seed) {
     CK(cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
     cudaFree(bad);
+    return (int)(h > 0x7fffffff ? 0x7fffffff : h);
+}
+// Miller loop of the shared-memory engine against the register engine's on the caller's items: number of differing 32-bit
+// words of f and of the encoding flags (0 = bit-identical)
+extern "C" int tcb_selftest_miller(tcb_ctx *ctx, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *dd) {
+    if (!ctx) return -2;
+    DevState &d = ctx->devs[0];
+    CK(cudaSetDevice(d.dev));
+    if (arena_reset(ctx, d)) return -1;
+    if (!n) return 0;
+    cudaStream_t st = d.stream;
+    u8 *da = up(ctx, d, a, 96 * n), *db = up(ctx, d, b, 192 * n), *dc = c ? up(ctx, d, c, 96 * n) : nullptr, *ddv = up(ctx, d, dd, 192 * n);
+    size_t fb = n * miller_f_bytes(), eb = (n + 3) & ~(size_t)3;
+    void *f1 = arena_alloc(ctx, d, fb), *f2 = arena_alloc(ctx, d, fb);
+    u8 *e1 = (u8 *)arena_alloc(ctx, d, eb), *e2 = (u8 *)arena_alloc(ctx, d, eb);
+    unsigned long long *bad = (unsigned long long *)arena_alloc(ctx, d, 8), h = 0;
+    if (!da || !db || (c && !dc) || !ddv || !f1 || !f2 || !e1 || !e2 || !bad) return -1;
+    CK(cudaMemsetAsync(bad, 0, 8, st));
+    CK(cudaMemsetAsync(e1, 0, eb, st));
+    CK(cudaMemsetAsync(e2, 0, eb, st));
+    RUN(run_miller_quad(st, n, da, db, dc, ddv, f1, e1));
+    RUN(run_miller_quad_reg(st, n, da, db, dc, ddv, f2, e2));
+    RUN(run_count_diff(st, fb, f1, f2, bad));
+    RUN(run_count_diff(st, eb, e1, e2, bad));
+    CK(cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return (int)(h > 0x7fffffff ? 0x7fffffff : h);
 }
 template <class F>
