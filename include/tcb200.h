@@ -54,6 +54,9 @@ int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups);
  * bound by global-memory latency at 2 warps per scheduler), 2 one scalar multiplication per share.  Same outputs;
  * 1 and 2 exist for measurement. */
 int tcb_set_msm_algo(tcb_ctx *ctx, int algo);
+/* Commitment::evaluate: units (coefficient blocks) per evaluation point.  0 (default) = chosen from the batch size (small batches
+ * are split so that they fill the GPU), 1 = never split, k > 1 = force k.  Same outputs. */
+int tcb_set_eval_split(tcb_ctx *ctx, size_t units);
 /* number of kernel launches issued through ctx since tcb_init (bench.py's gpu_launches) */
 uint64_t tcb_launch_count(const tcb_ctx *ctx);
 
@@ -121,6 +124,13 @@ int tcb_verify_g2_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *a_
                             const uint8_t *c_g1, const uint8_t *d_g2, uint8_t *ok);
 int tcb_hash_g2_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *msgs, const uint64_t *off,
                           uint8_t *out_g2);
+/* The two halves of tcb_verify_g2_batch_dev as separate launches (EXTERNAL pairing 0.16 Engine::miller_loop over the two pairs
+ * (a,b), (-c,d), then final_exponentiation(..) == 1): f_out / f_in hold tcb_miller_value_bytes() per item (opaque, device-side
+ * layout), enc_ok one byte per item (0 = some coordinate >= p).  bench.py times the two kernels through these. */
+int tcb_miller_loop_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *a_g1, const uint8_t *b_g2,
+                              const uint8_t *c_g1, const uint8_t *d_g2, void *f_out, uint8_t *enc_ok);
+int tcb_final_exp_is_one_batch_dev(tcb_ctx *, void *stream, size_t n, const void *f_in, const uint8_t *enc_ok, uint8_t *ok);
+size_t tcb_miller_value_bytes(void);
 int tcb_verify_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *pk_g1, const uint8_t *sig_g2,
                          const uint8_t *msgs, const uint64_t *off, uint8_t *ok);
 int tcb_sign_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *sk, const uint8_t *msgs,

@@ -51,6 +51,8 @@ extern "C" void tcb_emu_set_groups(size_t g) { g_groups = g ? g : 1; }
 extern "C" int tcb_set_msm_groups(tcb_ctx *, size_t g) { g_groups = g ? g : 2; return 0; }
 static int g_algo = 0;
 extern "C" int tcb_set_msm_algo(tcb_ctx *, int a) { g_algo = a; return 0; }
+static size_t g_eval_split = 0;
+extern "C" int tcb_set_eval_split(tcb_ctx *, size_t u) { g_eval_split = u > 1 ? u : 0; return 0; }
 template <class M, class JS>
 static void msm_acc_ba(size_t n, size_t m, size_t G, const typename M::PS *tab, const typename M::DG *dg, JS *part) {
     size_t cnt_max = (m + G - 1) / G;
@@ -124,6 +126,13 @@ extern "C" int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const u8 *sk, u8 *out) 
 extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
     std::vector<Aff1Store> tab(deg + 1);
     for (size_t c = 0; c <= deg; c++) task_g1_decode(c, coeff, tab.data());
+    if (g_eval_split > 1) {       // the split evaluation of small batches (coefficient blocks + x^(b L) recombination + sum)
+        size_t B = g_eval_split, L = (deg + B) / B;
+        std::vector<Jac1Store> terms(n * B);
+        for (size_t u = 0; u < n * B; u++) task_commit_eval_part(u, B, L, deg, tab.data(), x, terms.data());
+        for (size_t i = 0; i < n; i++) store_g1(out + 96 * i, g1_sum(i, B, terms.data()));
+        return 0;
+    }
     for (size_t i = 0; i < n; i++) task_commit_eval(i, deg, tab.data(), x, out);
     return 0;
 }

@@ -45,7 +45,17 @@ def test_no_cpu_fallback():
 
 
 def test_sass_is_sm100a_integer_code():
-    """The shipped cubin targets sm_100a and the Fp multiply is carry-chained IMAD.WIDE."""
+    """The shipped cubin targets sm_100a; the Fp multiply is carry-chained IMAD.WIDE (IMAD.WIDE.U32.X with predicate carries),
+    the shared-memory Miller kernel stages its operands with 128-bit LDS/STS and takes its inputs through the TMA unit (UBLKCP),
+    and there is no tensor-core instruction anywhere (integer modular arithmetic)."""
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", SO], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+    fn = "_Z13k_miller_quadmPKhS0_S0_S0_PN3tcb4MontINS1_8FpParamsEEEPh"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", fn, SO], capture_output=True, text=True).stdout
+    assert "Function : " + fn in sass
+    assert sass.count("IMAD.WIDE.U32.X") > 300, "carry-chained wide multiply-accumulates missing"
+    assert "UBLKCP" in sass, "bulk asynchronous (TMA) input staging missing"
+    assert sass.count("LDS.128") > 50 and sass.count("STS.128") > 50, "shared-memory operand staging missing"
+    for tensor_op in ("HMMA", "IMMA", "UTCHMMA", "UTCIMMA"):
+        assert tensor_op not in sass

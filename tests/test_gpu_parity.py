@@ -261,3 +261,105 @@ def test_both_pairing_engines_vs_oracle(gpu_engine, O):
         assert np.array_equal(d_ok.cpu().numpy(), exp)
     finally:
         E.set_engine(ENGINE_QUAD_SMEM)
+
+
+def _poly_shares(coeff_bytes, xs_ints):
+    """host big-int Horner: f(x) for every x (canonical 32-byte little-endian scalars)"""
+    from conftest import R
+    cs = [int.from_bytes(bytes(coeff_bytes[32 * k:32 * k + 32]), "little") for k in range(coeff_bytes.size // 32)]
+    out = []
+    for x in xs_ints:
+        acc = 0
+        for c in reversed(cs):
+            acc = (acc * x + c) % R
+        out.append(acc)
+    return out
+
+
+def test_config3_combine_full_size(gpu_engine, O):
+    """BASELINE config #3 at full size: combine_signatures t = 10 over 2^14 distinct messages (per-item signer subsets out of 32):
+    every item against the interpolation identity (the master signature), 512 items spread over the batch bit-exact against the
+    oracle's interpolate (src/lib.rs:719-767)."""
+    E = gpu_engine
+    n, t = 1 << 14, 10
+    m = t + 1
+    rng = np.random.default_rng(33)
+    poly = rand_fr(rng, m)
+    idx = np.stack([np.sort(rng.choice(32, size=m, replace=False)) for _ in range(n)])
+    sk32 = fr_bytes(_poly_shares(poly, [j + 1 for j in range(32)])).reshape(32, 32)
+    hm = E.hash_g2_batch([b"cfg3/%d" % i for i in range(n)])
+    shares = E.sign_g2_batch(sk32[idx.reshape(-1)].reshape(-1), np.repeat(hm, m, axis=0))
+    xs = fr_bytes([int(j) + 1 for j in idx.reshape(-1)])
+    out, st = E.combine_g2_batch(n, t, xs, shares)
+    assert not st.any() and np.array_equal(out, E.sign_g2_batch(np.tile(poly[:32], n), hm))
+    sel = np.sort(rng.choice(n, 512, replace=False))
+    O.set_threads(16)
+    xs_s = xs.reshape(n, m * 32)[sel].reshape(-1)
+    sh_s = shares.reshape(n, m, 192)[sel].reshape(-1, 192)
+    oo, ost = O.combine_g2_batch(len(sel), t, xs_s, sh_s)
+    O.set_threads(1)
+    assert np.array_equal(out[sel], oo) and not ost.any()
+
+
+def test_config4_decrypt_full_size(gpu_engine, O):
+    """BASELINE config #4: threshold decrypt t = 64 over 2^12 ciphertexts through tcb_decrypt_batch (src/lib.rs:618-626, test
+    :908-939): every plaintext must come back (encrypt -> 65 decryption shares -> decrypt identity) and 256 items are bit-exact
+    against the oracle's decrypt (interpolate::<G1> + xor_with_hash)."""
+    E = gpu_engine
+    n, t = 1 << 12, 64
+    m = t + 1
+    rng = np.random.default_rng(44)
+    poly = rand_fr(rng, m)
+    pkm = E.g1_mul_gen_batch(poly[:32])
+    rs = rand_fr(rng, n)
+    plains = [bytes(rng.integers(0, 256, size=64, dtype=np.uint8)) for _ in range(n)]
+    u, v, w = E.encrypt_batch(np.tile(pkm[0], (n, 1)), rs, plains)
+    assert E.verify_g2_batch(u, E.hash_g1_g2_batch(u, v), None, w).all()          # Ciphertext::verify on every item
+    sk_shares = fr_bytes(_poly_shares(poly, [j + 1 for j in range(m)]))
+    dshares = E.decrypt_share_batch(np.tile(sk_shares, n), np.repeat(u, m, axis=0))
+    xs = np.tile(fr_bytes([j + 1 for j in range(m)]), n)
+    dec, st = E.decrypt_batch(n, t, xs, dshares, v)
+    assert dec == plains and not st.any()
+    sel = np.sort(rng.choice(n, 256, replace=False))
+    O.set_threads(16)
+    odec, ost = O.decrypt_batch(len(sel), t, xs.reshape(n, m * 32)[sel].reshape(-1), dshares.reshape(n, m, 96)[sel].reshape(-1, 96), [v[i] for i in sel])
+    assert np.array_equal(O.decrypt_share_batch(np.tile(sk_shares, 4), np.repeat(u[:4], m, axis=0)), dshares[:4 * m])
+    O.set_threads(1)
+    assert odec == [plains[i] for i in sel] and not ost.any()
+
+
+def test_config5_commit_eval_full_size(gpu_engine, O):
+    """BASELINE config #5: Commitment::evaluate of a degree-1023 commitment at the 2^16 indices 1..65536 (src/poly.rs:497-508,
+    src/lib.rs:570-573): every output against f(x) * g1 (host Fr Horner + fixed-base multiplication), 512 points spread over the
+    range bit-exact against the oracle's Horner; the 8192-point call takes the split path (coefficient blocks) and must give the
+    same bytes; secondary run with 2^12 random 255-bit x."""
+    from conftest import R
+    E = gpu_engine
+    rng = np.random.default_rng(55)
+    coeff = rand_fr(rng, 1024)
+    comm = E.g1_mul_gen_batch(coeff)
+    n = 1 << 16
+    xs = fr_bytes([i + 1 for i in range(n)])
+    out = E.commitment_eval_batch(comm, xs)
+    assert np.array_equal(out, E.g1_mul_gen_batch(fr_bytes(_poly_shares(coeff, [i + 1 for i in range(n)]))))
+    sel = np.sort(np.concatenate([[0, 1, n - 2, n - 1], rng.choice(n, 508, replace=False)]))
+    O.set_threads(16)
+    assert np.array_equal(out[sel], O.commitment_eval_batch(comm, xs.reshape(n, 32)[sel].reshape(-1)))
+    # small batch -> split path; forced single-unit walk gives the same bytes
+    small = E.commitment_eval_batch(comm, xs[:8192 * 32])
+    assert np.array_equal(small, out[:8192])
+    try:
+        E.set_eval_split(1)
+        assert np.array_equal(E.commitment_eval_batch(comm, xs[:256 * 32]), out[:256])
+        E.set_eval_split(5)         # a block count that does not divide 1024
+        assert np.array_equal(E.commitment_eval_batch(comm, xs[:256 * 32]), out[:256])
+    finally:
+        E.set_eval_split(0)
+    # random full-size x
+    n2 = 1 << 12
+    xr_int = [int.from_bytes(rng.bytes(40), "little") % R for _ in range(n2)]
+    xr = fr_bytes(xr_int)
+    out2 = E.commitment_eval_batch(comm, xr)
+    assert np.array_equal(out2, E.g1_mul_gen_batch(fr_bytes(_poly_shares(coeff, xr_int))))
+    assert np.array_equal(out2[:16], O.commitment_eval_batch(comm, xr[:16 * 32]))
+    O.set_threads(1)

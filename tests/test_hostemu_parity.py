@@ -98,3 +98,20 @@ def test_dot_product_core(emu):
     non-canonical operand p)."""
     import ctypes as C
     assert emu.lib.tcb_emu_dotk_check(300, C.c_uint64(17)) == 0
+
+
+def test_commit_eval_split_blocks(emu, O):
+    """Commitment::evaluate with B units per point (coefficient blocks, recombined with x^(b L)): same bytes as the oracle's Horner
+    for B = 2, 3, 4 incl. blocks past the end (deg + 1 = 7 not divisible), x = 0 and a full-size x."""
+    import conftest
+    rng = np.random.default_rng(12)
+    coeff = conftest.rand_fr(rng, 7)
+    comm = O.g1_mul_gen_batch(coeff)
+    xs = fr_bytes([0, 1, 2, 65536, int.from_bytes(rng.bytes(40), "little")])
+    exp = O.commitment_eval_batch(comm, xs)
+    try:
+        for B in (2, 3, 4, 8):
+            emu.set_eval_split(B)
+            assert np.array_equal(emu.commitment_eval_batch(comm, xs), exp), B
+    finally:
+        emu.set_eval_split(0)

@@ -90,6 +90,10 @@ class Engine:
         """0 Straus / shared doublings (default), 1 batch-affine tree, 2 one multiplication per share."""
         self._ck(self.lib.tcb_set_msm_algo(self.ctx, int(algo)))
 
+    def set_eval_split(self, units):
+        """Units per point of Commitment::evaluate: 0 auto, 1 never split, k forced."""
+        self._ck(self.lib.tcb_set_eval_split(self.ctx, C.c_size_t(int(units))))
+
     def launch_count(self):
         return int(self.lib.tcb_launch_count(self.ctx))
 

@@ -77,6 +77,11 @@ __global__ void __launch_bounds__(128, 4) k_commit_eval(size_t n, size_t deg, co
     if (i < n) task_commit_eval(i, deg, coeff, x, out);
 }
 
+__global__ void __launch_bounds__(128, 4) k_commit_eval_part(size_t units, size_t B, size_t L, size_t deg, const Aff1Store *coeff, const u8 *x, Jac1Store *out) {
+    size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < units) task_commit_eval_part(u, B, L, deg, coeff, x, out);
+}
+
 static __device__ __forceinline__ u64 splitmix(u64 &s) {
     u64 z = (s += 0x9e3779b97f4a7c15ULL);
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
@@ -198,6 +203,14 @@ void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab) {
 }
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out) {
     if (n) k_commit_eval<<<grid1(n), 128, 0, st>>>(n, deg, (const Aff1Store *)tab, x, out);
+}
+size_t commit_eval_units_per_sm() {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_commit_eval_part, 128, 0) != cudaSuccess || blocks < 1) blocks = 1;
+    return (size_t)blocks * 128;
+}
+void run_commit_eval_part(cudaStream_t st, size_t n, size_t B, size_t L, size_t deg, const void *tab, const u8 *x, void *terms) {
+    if (n * B) k_commit_eval_part<<<grid1(n * B), 128, 0, st>>>(n * B, B, L, deg, (const Aff1Store *)tab, x, (Jac1Store *)terms);
 }
 void run_encrypt_uv(cudaStream_t st, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out) {
     if (n) k_encrypt_uv<<<grid1(n), 128, 0, st>>>(n, pk, r, msgs, off, u_out, v_out);

@@ -67,6 +67,8 @@ void run_g1_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const 
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);
+size_t commit_eval_units_per_sm();
+void run_commit_eval_part(cudaStream_t st, size_t n, size_t B, size_t L, size_t deg, const void *tab, const u8 *x, void *terms);   // then run_g1_sum(n, B, ...)
 void run_encrypt_uv(cudaStream_t st, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out);
 void run_g1_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out);
 void run_g1_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status);

@@ -27,23 +27,58 @@ template <class F2> TCB_HD u32 my_role() {
 
 // ----------------------------------------------------------------------------- codecs
 // 48-byte big-endian canonical -> Montgomery.  ok=false if the integer is >= p.
-TCB_HD Fp load_fp_be(const u8 *b, bool &ok) {
-    Fp t;
+// On the device a 16-byte aligned source is read as three 128-bit vectors and byte-swapped with PRMT (the ABI's arrays
+// are 16-byte aligned whenever the caller's base pointer is: every record size is a multiple of 16); anything else (and the
+// host emulation) takes the byte loop.
+TCB_HD u32 bswap32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+#endif
+}
+TCB_HD void load_limbs_be(u32 *l, const u8 *b) {
+#if defined(__CUDA_ARCH__)
+    if ((((size_t)b) & 15) == 0) {
+        const uint4 *p = (const uint4 *)b;
+        uint4 v0 = p[0], v1 = p[1], v2 = p[2];
+        l[11] = bswap32(v0.x); l[10] = bswap32(v0.y); l[9] = bswap32(v0.z); l[8] = bswap32(v0.w);
+        l[7] = bswap32(v1.x); l[6] = bswap32(v1.y); l[5] = bswap32(v1.z); l[4] = bswap32(v1.w);
+        l[3] = bswap32(v2.x); l[2] = bswap32(v2.y); l[1] = bswap32(v2.z); l[0] = bswap32(v2.w);
+        return;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         const u8 *q = b + (11 - i) * 4;
-        t.l[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+        l[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
     }
+}
+TCB_HD void store_limbs_be(u8 *b, const u32 *l) {
+#if defined(__CUDA_ARCH__)
+    if ((((size_t)b) & 15) == 0) {
+        uint4 *p = (uint4 *)b;
+        p[0] = make_uint4(bswap32(l[11]), bswap32(l[10]), bswap32(l[9]), bswap32(l[8]));
+        p[1] = make_uint4(bswap32(l[7]), bswap32(l[6]), bswap32(l[5]), bswap32(l[4]));
+        p[2] = make_uint4(bswap32(l[3]), bswap32(l[2]), bswap32(l[1]), bswap32(l[0]));
+        return;
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        u8 *q = b + (11 - i) * 4;
+        q[0] = (u8)(l[i] >> 24); q[1] = (u8)(l[i] >> 16); q[2] = (u8)(l[i] >> 8); q[3] = (u8)l[i];
+    }
+}
+TCB_HD Fp load_fp_be(const u8 *b, bool &ok) {
+    Fp t;
+    load_limbs_be(t.l, b);
     ok = ok && limbs_lt_mod<FpParams>(t.l);
     return fp_to_mont(t);
 }
 TCB_HD void store_fp_be(u8 *b, const Fp &a) {
     Fp t = fp_from_mont(a);
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        u8 *q = b + (11 - i) * 4;
-        q[0] = (u8)(t.l[i] >> 24); q[1] = (u8)(t.l[i] >> 16); q[2] = (u8)(t.l[i] >> 8); q[3] = (u8)t.l[i];
-    }
+    store_limbs_be(b, t.l);
 }
 // G1 uncompressed 96 B: x || y, byte0 bit 0x40 = infinity
 TCB_HD Aff<Fp> load_g1(const u8 *b, bool &ok) {
@@ -102,6 +137,14 @@ TCB_HD void store_g2(u8 *b, const Aff<F2> &a) {
 }
 // canonical LE 32-byte scalar -> 8 u32 limbs (no reduction; caller guarantees < r or accepts k mod group order)
 TCB_HD void load_scalar_le(u32 *k, const u8 *b) {
+#if defined(__CUDA_ARCH__)
+    if ((((size_t)b) & 15) == 0) {       // two 128-bit loads
+        const uint4 *p = (const uint4 *)b;
+        uint4 v0 = p[0], v1 = p[1];
+        k[0] = v0.x; k[1] = v0.y; k[2] = v0.z; k[3] = v0.w; k[4] = v1.x; k[5] = v1.y; k[6] = v1.z; k[7] = v1.w;
+        return;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) k[i] = (u32)b[4 * i] | ((u32)b[4 * i + 1] << 8) | ((u32)b[4 * i + 2] << 16) | ((u32)b[4 * i + 3] << 24);
 }
@@ -792,25 +835,61 @@ TCB_HD Aff<Fp> aff1_load(const Aff1Store &e) {
     t.inf = e.x.is_zero() && e.y.is_zero();
     return t;
 }
+// index of the leading one of a 256-bit scalar (-1 for zero)
+TCB_HD int scalar_top_bit(const u32 *k) {
+    for (int b = 255; b >= 0; b--)
+        if ((k[b >> 5] >> (b & 31)) & 1) return b;
+    return -1;
+}
+// one Horner step acc <- acc * x + C
+TCB_HD Jac<Fp> commit_eval_step(const Jac<Fp> &acc_in, const u32 *k, int top, const Aff<Fp> &c) {
+    Jac<Fp> acc = acc_in;
+    if (top < 0) acc = jac_inf<Fp>();
+    else {
+        Jac<Fp> base = acc;
+        for (int b = top - 1; b >= 0; b--) {
+            acc = jac_dbl(acc);
+            if ((k[b >> 5] >> (b & 31)) & 1) acc = jac_add(acc, base);
+        }
+    }
+    return jac_add_mixed(acc, c);
+}
 TCB_HD void task_commit_eval(size_t i, size_t deg, const Aff1Store *coeff, const u8 *x_fr, u8 *out_g1) {
     u32 k[8];
     load_scalar_le(k, x_fr + 32 * i);
-    int top = -1;                                  // index of the leading one of x
-    for (int b = 255; b >= 0; b--)
-        if ((k[b >> 5] >> (b & 31)) & 1) { top = b; break; }
+    int top = scalar_top_bit(k);
     Jac<Fp> acc = jac_from_aff(aff1_load(coeff[deg]));
-    for (size_t c = deg; c-- > 0;) {
-        if (top < 0) acc = jac_inf<Fp>();
-        else {
-            Jac<Fp> base = acc;
-            for (int b = top - 1; b >= 0; b--) {
-                acc = jac_dbl(acc);
-                if ((k[b >> 5] >> (b & 31)) & 1) acc = jac_add(acc, base);
-            }
-        }
-        acc = jac_add_mixed(acc, aff1_load(coeff[c]));
-    }
+    for (size_t c = deg; c-- > 0;) acc = commit_eval_step(acc, k, top, aff1_load(coeff[c]));
     store_g1(out_g1 + 96 * i, jac_to_aff(acc));
+}
+// The same evaluation with B units per point (small batches: one thread per point walks deg dependent Horner steps and
+// leaves most of the GPU idle).  Unit (i, b) evaluates the coefficient block [b L, (b+1) L) by Horner and multiplies its partial
+// sum by x^(b L) mod r (Fr power, then one 255-bit double-and-add), so that sum_b part_{i,b} is the value; the B terms are added by
+// k_g1_sum.  Same group element, hence the same output bytes, as the single-unit walk.
+TCB_HD void task_commit_eval_part(size_t u, size_t B, size_t L, size_t deg, const Aff1Store *coeff, const u8 *x_fr, Jac1Store *out) {
+    size_t i = u / B, b = u % B;
+    size_t lo = b * L, hi = lo + L < deg + 1 ? lo + L : deg + 1;       // coefficients [lo, hi)
+    Jac<Fp> acc = jac_inf<Fp>();
+    if (lo <= deg) {
+        u32 k[8];
+        load_scalar_le(k, x_fr + 32 * i);
+        int top = scalar_top_bit(k);
+        acc = jac_from_aff(aff1_load(coeff[hi - 1]));
+        for (size_t c = hi - 1; c-- > lo;) acc = commit_eval_step(acc, k, top, aff1_load(coeff[c]));
+        if (b) {
+            bool ok = true;
+            Fr xm = fr_load_le(x_fr + 32 * i, ok), s = fr_one();
+            int tb = 63;
+            while (tb > 0 && !((lo >> tb) & 1)) tb--;
+            for (int j = tb; j >= 0; j--) {
+                s = s * s;
+                if ((lo >> j) & 1) s = s * xm;
+            }
+            Fr sc = from_mont<FrParams>(s);
+            acc = jac_mul_jac<Fp, 8>(acc, sc.l);
+        }
+    }
+    store_jac(out[u], acc);
 }
 // §8(f) row 2, PublicKey::encrypt_with_rng (src/lib.rs:128-137) with the random scalar r supplied by
 // the caller: u = g1 * r, v = xor_with_hash(pk * r, msg).  (w = hash_g1_g2(u, v) * r is produced by

@@ -33,17 +33,24 @@ using namespace tcbk;
 struct Chunk { void *p; size_t sz, used; };
 struct DevState {
     int dev;
-    cudaStream_t stream;
+    cudaStream_t stream, stream2;      // host-buffer calls alternate the chunks of a large batch between the two (copy k+1 overlaps compute k)
+    cudaStream_t cur_stream = nullptr; // stream of the piece being enqueued (up / down)
+    cudaEvent_t last_ev = nullptr;     // end of the last call that used the scratch arena: the next call's stream waits on it
+    bool has_last = false;
     std::vector<Chunk> chunks;
     size_t high_water = 0, cur = 0;
 };
+struct Download { size_t g; cudaStream_t st; void *host; const void *dev; size_t bytes; };
 struct tcb_ctx {
     std::vector<DevState> devs;
     std::string err;
+    std::vector<Download> pending;  // device -> host copies of the running host-buffer call, enqueued after every device has its work
     uint64_t launches = 0;
     int engine = TCB_ENGINE_QUAD_SMEM;
     int sm_count = 148;
     size_t msm_groups = 0;          // 0 = auto (pick_groups)
+    size_t eval_split = 0;          // units per point of Commitment::evaluate: 0 = auto (tcb_set_eval_split)
+    bool eval_split_off = false;
     int msm_algo = 0;               // MSM_STRAUS (default) | MSM_BATCH_AFFINE | MSM_PER_SHARE (tcb_set_msm_algo; the others are measurement knobs)
 };
 
@@ -239,7 +246,21 @@ static int impl_commit_eval(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t d
     void *tab = arena_alloc(ctx, d, (deg + 1) * g1_term_bytes());
     if (!tab) return -1;
     RUN(run_g1_decode(st, deg + 1, coeff, tab));
-    if (n) RUN(run_commit_eval(st, n, deg, tab, x, out));
+    if (!n) return 0;
+    // Small batches: B units per point (coefficient blocks) so that the evaluation fills the GPU; each block keeps >= 32 coefficients
+    // so that the 255-bit recombination multiply stays a small part of the unit's work.
+    static size_t per_sm = 0;
+    if (!per_sm) per_sm = commit_eval_units_per_sm();
+    size_t resident = per_sm * (size_t)ctx->sm_count, B = 1;
+    if (!ctx->eval_split_off)
+        while (B < 16 && n * B * 2 <= resident && (deg + 1) / (B * 2) >= 32) B *= 2;
+    if (ctx->eval_split) B = ctx->eval_split;
+    if (B <= 1) { RUN(run_commit_eval(st, n, deg, tab, x, out)); return 0; }
+    size_t L = (deg + B) / B;                                   // ceil((deg + 1) / B)
+    void *terms = arena_alloc(ctx, d, n * B * g1_term_bytes());
+    if (!terms) return -1;
+    RUN(run_commit_eval_part(st, n, B, L, deg, tab, x, terms));
+    RUN(run_g1_sum(st, n, B, terms, out));
     return 0;
 }
 
@@ -266,7 +287,9 @@ extern "C" int tcb_init(tcb_ctx **out, const int *device_ids, int n_devices) {
     for (auto &d : ctx->devs) {
         if (d.dev < 0 || d.dev >= count) { delete ctx; return -4; }
         if (cudaSetDevice(d.dev) != cudaSuccess) { delete ctx; return -5; }
-        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -6; }
+        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.last_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return -6; }
         if (upload_consts_pairing(C) != cudaSuccess || upload_consts_miller(C) != cudaSuccess || upload_consts_g2(C) != cudaSuccess ||
             upload_consts_g1(C) != cudaSuccess) { delete ctx; return -7; }
     }
@@ -281,11 +304,15 @@ extern "C" void tcb_free(tcb_ctx *ctx) {
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
+        cudaStreamSynchronize(d.stream2);
+        if (d.has_last) cudaEventSynchronize(d.last_ev);
         for (auto &c : d.chunks) {
             cudaMemset(c.p, 0, c.sz);   // scratch may have held secret scalars (src/lib.rs:304-314 hygiene)
             cudaFree(c.p);
         }
         cudaStreamDestroy(d.stream);
+        cudaStreamDestroy(d.stream2);
+        cudaEventDestroy(d.last_ev);
     }
     delete ctx;
 }
@@ -300,6 +327,12 @@ extern "C" int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups) {
     ctx->msm_groups = groups;
     return 0;
 }
+extern "C" int tcb_set_eval_split(tcb_ctx *ctx, size_t units) {
+    if (!ctx || units > 64) return -2;
+    ctx->eval_split = units > 1 ? units : 0;
+    ctx->eval_split_off = units == 1;
+    return 0;
+}
 extern "C" int tcb_set_msm_algo(tcb_ctx *ctx, int algo) {
     if (!ctx || algo < 0 || algo > 3) return -2;
     ctx->msm_algo = algo;
@@ -308,82 +341,133 @@ extern "C" int tcb_set_msm_algo(tcb_ctx *ctx, int algo) {
 extern "C" uint64_t tcb_launch_count(const tcb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 // ----------------------------------------------------------------------------- _dev API (device pointers, caller's stream)
-#define DEV_PROLOGUE                         \
-    if (!ctx) return -2;                     \
-    DevState &d = ctx->devs[0];              \
-    cudaStream_t st = (cudaStream_t)stream;  \
-    CK(cudaSetDevice(d.dev));                \
-    if (arena_reset(ctx, d)) return -1;
+// The scratch arena is reused from call to call: a call on another stream first waits (on the device) for the end of the
+// previous call, so consecutive _dev calls on one ctx may use different streams.
+#define DEV_PROLOGUE                                                     \
+    if (!ctx) return -2;                                                 \
+    DevState &d = ctx->devs[0];                                          \
+    cudaStream_t st = (cudaStream_t)stream;                              \
+    CK(cudaSetDevice(d.dev));                                            \
+    if (arena_reset(ctx, d)) return -1;                                  \
+    if (d.has_last) CK(cudaStreamWaitEvent(st, d.last_ev, 0));
+#define DEV_RETURN(expr)                                                 \
+    do {                                                                 \
+        int rc_ = (expr);                                                \
+        if (rc_ == 0) { CK(cudaEventRecord(d.last_ev, st)); d.has_last = true; } \
+        return rc_;                                                      \
+    } while (0)
 
 extern "C" int tcb_verify_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *dd, u8 *ok) {
     DEV_PROLOGUE
-    return impl_verify_g2(ctx, d, st, n, a, b, c, dd, ok);
+    DEV_RETURN(impl_verify_g2(ctx, d, st, n, a, b, c, dd, ok));
 }
+// the two halves of the pairing check on their own (bench.py times each kernel separately; also the batched form of the
+// pairing engine's miller_loop / final_exponentiation pair): f = 576 B per item, Montgomery form, quad-sliced
+extern "C" int tcb_miller_loop_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *dd, void *f_out, u8 *enc_ok) {
+    DEV_PROLOGUE
+    if (n) {
+        if (ctx->engine == TCB_ENGINE_QUAD_REG) RUN(run_miller_quad_reg(st, n, a, b, c, dd, f_out, enc_ok));
+        else RUN(run_miller_quad(st, n, a, b, c, dd, f_out, enc_ok));
+    }
+    DEV_RETURN(0);
+}
+extern "C" int tcb_final_exp_is_one_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const void *f_in, const u8 *enc_ok, u8 *ok) {
+    DEV_PROLOGUE
+    if (n) RUN(run_final_exp_quad(st, n, f_in, enc_ok, ok));
+    DEV_RETURN(0);
+}
+extern "C" size_t tcb_miller_value_bytes(void) { return miller_f_bytes(); }
 extern "C" int tcb_hash_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     DEV_PROLOGUE
-    return impl_hash_g2(ctx, st, n, msgs, off, out);
+    DEV_RETURN(impl_hash_g2(ctx, st, n, msgs, off, out));
 }
 extern "C" int tcb_verify_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     DEV_PROLOGUE
-    return impl_verify(ctx, d, st, n, pk, sig, msgs, off, ok);
+    DEV_RETURN(impl_verify(ctx, d, st, n, pk, sig, msgs, off, ok));
 }
 extern "C" int tcb_sign_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     DEV_PROLOGUE
-    return impl_sign(ctx, st, n, sk, msgs, off, h, out);
+    DEV_RETURN(impl_sign(ctx, st, n, sk, msgs, off, h, out));
 }
 extern "C" int tcb_combine_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     DEV_PROLOGUE
-    return impl_combine_g2(ctx, d, st, n, t, x, shares, out, status);
+    DEV_RETURN(impl_combine_g2(ctx, d, st, n, t, x, shares, out, status));
 }
 extern "C" int tcb_combine_g1_batch_dev(tcb_ctx *ctx, void *stream, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     DEV_PROLOGUE
-    return impl_combine_g1(ctx, d, st, n, t, x, shares, out, status, 0, nullptr, nullptr);
+    DEV_RETURN(impl_combine_g1(ctx, d, st, n, t, x, shares, out, status, 0, nullptr, nullptr));
 }
 extern "C" int tcb_decrypt_batch_dev(tcb_ctx *ctx, void *stream, size_t n, size_t t, const u8 *x, const u8 *shares, const u8 *v,
                                      const u64 *voff, u64 v_total, u8 *out, u8 *status) {
     DEV_PROLOGUE
     (void)v_total;
-    return impl_combine_g1(ctx, d, st, n, t, x, shares, out, status, 1, v, voff);
+    DEV_RETURN(impl_combine_g1(ctx, d, st, n, t, x, shares, out, status, 1, v, voff));
 }
 extern "C" int tcb_g1_mul_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *sk, const u8 *pts, u8 *out) {
     DEV_PROLOGUE
     if (n) RUN(run_g1_mul(st, n, sk, pts, out));
-    return 0;
+    DEV_RETURN(0);
 }
 extern "C" int tcb_commitment_eval_batch_dev(tcb_ctx *ctx, void *stream, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
     DEV_PROLOGUE
-    return impl_commit_eval(ctx, d, st, deg, coeff, n, x, out);
+    DEV_RETURN(impl_commit_eval(ctx, d, st, deg, coeff, n, x, out));
 }
 
 // ----------------------------------------------------------------------------- host-buffer API: shard over ctx's devices
 // Every item is independent: device g gets the contiguous slice [lo_g, hi_g) of
 // each per-item array; H2D, kernels and D2H are queued per device, then all are awaited.
 struct Slice { size_t lo, hi; };
-static Slice slice_of(size_t n, size_t g, size_t G) { return {n * g / G, n * (g + 1) / G}; }
 
 template <class T>
 static T *up(tcb_ctx *ctx, DevState &d, const T *host, size_t count) {
     T *p = (T *)arena_alloc(ctx, d, count * sizeof(T));
     if (!p) return nullptr;
-    if (count && cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, d.stream) != cudaSuccess) {
+    if (count && cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, d.cur_stream ? d.cur_stream : d.stream) != cudaSuccess) {
         ctx->err = "H2D copy failed";
         return nullptr;
     }
     return p;
 }
+// Results are copied back in a SECOND pass (sync_all), after every device and chunk has its uploads and kernels queued: a
+// device-to-host copy into pageable memory blocks the calling thread until that stream has drained, which would otherwise run
+// the devices one after the other.  With pinned caller buffers every copy is asynchronous.
 static int down(tcb_ctx *ctx, DevState &d, void *host, const void *dev, size_t bytes) {
-    if (bytes) CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, d.stream));
+    if (bytes) ctx->pending.push_back({(size_t)(&d - ctx->devs.data()), d.cur_stream ? d.cur_stream : d.stream, host, dev, bytes});
     return 0;
 }
 static int sync_all(tcb_ctx *ctx) {
     int rc = 0;
+    for (auto &dl : ctx->pending) {
+        cudaSetDevice(ctx->devs[dl.g].dev);
+        cudaError_t e = cudaMemcpyAsync(dl.host, dl.dev, dl.bytes, cudaMemcpyDeviceToHost, dl.st);
+        if (e != cudaSuccess) { ctx->err = std::string("D2H copy: ") + cudaGetErrorString(e); rc = -1; }
+    }
+    ctx->pending.clear();
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.dev);
-        cudaError_t e = cudaStreamSynchronize(d.stream);
-        if (e != cudaSuccess) { ctx->err = std::string("stream sync: ") + cudaGetErrorString(e); rc = -1; }
+        for (cudaStream_t st : {d.stream, d.stream2}) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { ctx->err = std::string("stream sync: ") + cudaGetErrorString(e); rc = -1; }
+        }
+        d.cur_stream = nullptr;
     }
     cudaSetDevice(ctx->devs[0].dev);
     return rc;
+}
+// A host batch is cut into pieces: one contiguous slice per device, and a large slice into up to four chunks that
+// alternate between the device's two streams.
+struct Piece { size_t g, lo, hi; int sidx; };
+static std::vector<Piece> make_pieces(tcb_ctx *ctx, size_t n, size_t grain) {
+    std::vector<Piece> out;
+    size_t G = ctx->devs.size();
+    for (size_t g = 0; g < G; g++) {
+        size_t lo = n * g / G, hi = n * (g + 1) / G, cnt = hi - lo;
+        if (!cnt) continue;
+        size_t chunks = grain ? cnt / grain : 1;
+        chunks = chunks < 1 ? 1 : (chunks > 4 ? 4 : chunks);
+        for (size_t k = 0; k < chunks; k++) out.push_back({g, lo + cnt * k / chunks, lo + cnt * (k + 1) / chunks, (int)(k & 1)});
+    }
+    return out;
 }
 // upload the message slice [lo,hi) with rebased offsets; keeps the rebased offsets alive in `keep`
 static int up_msgs(tcb_ctx *ctx, DevState &d, const u8 *msgs, const u64 *off, size_t lo, size_t hi,
@@ -396,19 +480,28 @@ static int up_msgs(tcb_ctx *ctx, DevState &d, const u8 *msgs, const u64 *off, si
     d_off = up(ctx, d, o.data(), o.size());
     return (d_msgs && d_off) ? 0 : -1;
 }
-#define HOST_PROLOGUE   \
-    if (!ctx) return -2; \
-    size_t G = ctx->devs.size();
+// GRAIN: items per chunk below which a device's slice is not split (0 = never split)
+#define HOST_PROLOGUE_G(GRAIN)                                                  \
+    if (!ctx) return -2;                                                        \
+    ctx->pending.clear();                                                       \
+    for (auto &dv_ : ctx->devs) {                                               \
+        CK(cudaSetDevice(dv_.dev));                                             \
+        if (arena_reset(ctx, dv_)) return -1;                                   \
+        if (dv_.has_last) {                                                     \
+            CK(cudaStreamWaitEvent(dv_.stream, dv_.last_ev, 0));                \
+            CK(cudaStreamWaitEvent(dv_.stream2, dv_.last_ev, 0));               \
+        }                                                                       \
+    }                                                                           \
+    std::vector<Piece> pieces = make_pieces(ctx, n, GRAIN);
+#define HOST_PROLOGUE HOST_PROLOGUE_G(0)
 #define FOR_EACH_DEV                                        \
-    for (size_t g = 0; g < G; g++) {                        \
-        DevState &d = ctx->devs[g];                         \
-        Slice s = slice_of(n, g, G);                        \
+    for (const Piece &pc_ : pieces) {                       \
+        DevState &d = ctx->devs[pc_.g];                     \
+        Slice s{pc_.lo, pc_.hi};                            \
         size_t cnt = s.hi - s.lo;                           \
         CK(cudaSetDevice(d.dev));                           \
-        if (arena_reset(ctx, d)) return -1;                 \
-        if (cnt == 0) continue;                             \
-        cudaStream_t st = d.stream;                         \
-        (void)st;
+        cudaStream_t st = pc_.sidx ? d.stream2 : d.stream;  \
+        d.cur_stream = st;
 #define END_FOR_EACH_DEV }
 
 extern "C" int tcb_verify_g2_batch(tcb_ctx *ctx, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *dd, u8 *ok) {
@@ -426,7 +519,7 @@ extern "C" int tcb_verify_g2_batch(tcb_ctx *ctx, size_t n, const u8 *a, const u8
 extern "C" int tcb_hash_g2_batch(tcb_ctx *ctx, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     HOST_PROLOGUE
     std::vector<std::vector<u64>> keep;
-    keep.reserve(G);
+    keep.reserve(pieces.size());
     FOR_EACH_DEV
         u8 *dm; u64 *doff;
         if (up_msgs(ctx, d, msgs, off, s.lo, s.hi, keep, dm, doff)) return -1;
@@ -440,7 +533,7 @@ extern "C" int tcb_hash_g2_batch(tcb_ctx *ctx, size_t n, const u8 *msgs, const u
 extern "C" int tcb_hash_g1_g2_batch(tcb_ctx *ctx, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
     HOST_PROLOGUE
     std::vector<std::vector<u64>> keep;
-    keep.reserve(G);
+    keep.reserve(pieces.size());
     FOR_EACH_DEV
         u8 *dm; u64 *doff;
         if (up_msgs(ctx, d, msgs, off, s.lo, s.hi, keep, dm, doff)) return -1;
@@ -455,7 +548,7 @@ extern "C" int tcb_hash_g1_g2_batch(tcb_ctx *ctx, size_t n, const u8 *g1, const 
 extern "C" int tcb_verify_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     HOST_PROLOGUE
     std::vector<std::vector<u64>> keep;
-    keep.reserve(G);
+    keep.reserve(pieces.size());
     FOR_EACH_DEV
         u8 *dm; u64 *doff;
         if (up_msgs(ctx, d, msgs, off, s.lo, s.hi, keep, dm, doff)) return -1;
@@ -470,7 +563,7 @@ extern "C" int tcb_verify_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 *
 static int sign_common(tcb_ctx *ctx, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     HOST_PROLOGUE
     std::vector<std::vector<u64>> keep;
-    keep.reserve(G);
+    keep.reserve(pieces.size());
     FOR_EACH_DEV
         u8 *dm = nullptr, *dh = nullptr; u64 *doff = nullptr;
         if (h) { dh = up(ctx, d, h + 192 * s.lo, 192 * cnt); if (!dh) return -1; }
@@ -491,7 +584,7 @@ extern "C" int tcb_sign_g2_batch(tcb_ctx *ctx, size_t n, const u8 *sk, const u8 
     return sign_common(ctx, n, sk, nullptr, nullptr, h, out);
 }
 extern "C" int tcb_combine_g2_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
-    HOST_PROLOGUE
+    HOST_PROLOGUE_G(4096)
     size_t m = t + 1;
     FOR_EACH_DEV
         u8 *dx = up(ctx, d, x + 32 * m * s.lo, 32 * m * cnt), *dsh = up(ctx, d, shares + 192 * m * s.lo, 192 * m * cnt);
@@ -503,7 +596,7 @@ extern "C" int tcb_combine_g2_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *
     return sync_all(ctx);
 }
 extern "C" int tcb_combine_g1_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
-    HOST_PROLOGUE
+    HOST_PROLOGUE_G(2048)
     size_t m = t + 1;
     FOR_EACH_DEV
         u8 *dx = up(ctx, d, x + 32 * m * s.lo, 32 * m * cnt), *dsh = up(ctx, d, shares + 96 * m * s.lo, 96 * m * cnt);
@@ -516,10 +609,10 @@ extern "C" int tcb_combine_g1_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *
 }
 extern "C" int tcb_decrypt_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *x, const u8 *shares, const u8 *v, const u64 *voff,
                                  u8 *out, u8 *status) {
-    HOST_PROLOGUE
+    HOST_PROLOGUE_G(1024)
     size_t m = t + 1;
     std::vector<std::vector<u64>> keep;
-    keep.reserve(G);
+    keep.reserve(pieces.size());
     FOR_EACH_DEV
         u8 *dv; u64 *dvoff;
         if (up_msgs(ctx, d, v, voff, s.lo, s.hi, keep, dv, dvoff)) return -1;
@@ -566,20 +659,25 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *ctx, size_t deg, const u8 *coe
 // ---- out_i = sum_k s_{i,k} P_{i,k}  (BivarCommitment::row / evaluate, src/poly.rs:693-726:
 // the caller supplies the Fr power products as scalars).  Same per-term + sum kernels as interpolate.
 static int lincomb_common(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out, int g2) {
-    HOST_PROLOGUE
+    HOST_PROLOGUE_G(2048)
     size_t pw = g2 ? 192 : 96;
     if (m == 0) { if (ctx) ctx->err = "m must be >= 1"; return -2; }
+    std::vector<u8> hstatus(n, 0);
     FOR_EACH_DEV
         u8 *dsc = up(ctx, d, scalars + 32 * m * s.lo, 32 * m * cnt), *dp = up(ctx, d, pts + pw * m * s.lo, pw * m * cnt);
         u8 *dout = (u8 *)arena_alloc(ctx, d, pw * cnt), *dst = (u8 *)arena_alloc(ctx, d, cnt);
         if (!dsc || !dp || !dout || !dst) return -1;
+        CK(cudaMemsetAsync(dst, 0, cnt, st));
         // canonical little-endian scalars are exactly the limb layout the recoding reads
         void *part; size_t Gp;
         if (g2) { if (impl_msm_g2(ctx, d, st, cnt, m, (const u32 *)dsc, dp, dst, part, Gp)) return -1; RUN(run_g2_sum(st, cnt, Gp, part, dout)); }
         else { if (impl_msm_g1(ctx, d, st, cnt, m, (const u32 *)dsc, dp, dst, part, Gp)) return -1; RUN(run_g1_sum(st, cnt, Gp, part, dout)); }
-        if (down(ctx, d, out + pw * s.lo, dout, pw * cnt)) return -1;
+        if (down(ctx, d, out + pw * s.lo, dout, pw * cnt) || down(ctx, d, hstatus.data() + s.lo, dst, cnt)) return -1;
     END_FOR_EACH_DEV
-    return sync_all(ctx);
+    if (sync_all(ctx)) return -1;
+    for (size_t i = 0; i < n; i++)
+        if (hstatus[i]) { ctx->err = "lincomb: item " + std::to_string(i) + " holds a point whose field element is >= p (invalid encoding)"; return -10; }
+    return 0;
 }
 extern "C" int tcb_g1_lincomb_batch(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out) { return lincomb_common(ctx, n, m, scalars, pts, out, 0); }
 extern "C" int tcb_g2_lincomb_batch(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out) { return lincomb_common(ctx, n, m, scalars, pts, out, 1); }
@@ -589,7 +687,7 @@ extern "C" int tcb_encrypt_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 
                                  u8 *u_out, u8 *v_out, u8 *w_out) {
     HOST_PROLOGUE
     std::vector<std::vector<u64>> keep;
-    keep.reserve(G);
+    keep.reserve(pieces.size());
     FOR_EACH_DEV
         u8 *dm; u64 *doff;
         if (up_msgs(ctx, d, msgs, off, s.lo, s.hi, keep, dm, doff)) return -1;
