@@ -523,13 +523,17 @@ def run_gpu(args):
             if rank == 0 and torch.cuda.device_count() >= 2:
                 E2 = Engine(devices=[0, 1])
                 xs_np, sh_np = xs.numpy(), sh.numpy()
-                o2, s2 = E2.combine_g2_batch(nc, t, xs_np, sh_np)
-                t0 = time.perf_counter()
-                o2, s2 = E2.combine_g2_batch(nc, t, xs_np, sh_np)
-                dt2 = time.perf_counter() - t0
-                t0 = time.perf_counter()
-                o1, s1 = E.combine_g2_batch(nc, t, xs_np, sh_np)
-                dt1 = time.perf_counter() - t0
+                def best_of(eng, reps=3):
+                    best = 1e9
+                    for _ in range(reps):
+                        t0 = time.perf_counter()
+                        r = eng.combine_g2_batch(nc, t, xs_np, sh_np)
+                        best = min(best, time.perf_counter() - t0)
+                    return best, r
+                for _ in range(2):                       # warm-up: the scratch arena settles after the second call
+                    E2.combine_g2_batch(nc, t, xs_np, sh_np)
+                dt2, (o2, s2) = best_of(E2)
+                dt1, (o1, s1) = best_of(E)
                 ok2 = E2.verify_batch(pk[:4096], sig[:4096], msgs[:4096])
                 assert np.array_equal(o2, ref_out) and np.array_equal(s2, ref_st) and np.array_equal(ok2, expect[:4096]), "two-device ctx output differs"
                 multi_ctx = {"devices": 2, "combine_ms_two_devices": 1e3 * dt2, "combine_ms_one_device": 1e3 * dt1, "bit_exact": True,

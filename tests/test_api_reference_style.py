@@ -139,3 +139,27 @@ def test_poly_algebra(tc):                    # src/poly.rs:783-797 incl. interp
     for x, y in samples:
         assert poly.evaluate(x) == y % tc.R
     assert tc.Poly.interpolate(samples) == poly
+
+
+def test_checked_from_bytes_and_size_errors(tc):
+    """PublicKey / Signature can only come from the checked decoder (src/lib.rs:140-146, 246-252): round trip through the
+    48 / 96-byte wire format, FromBytesError for a tampered encoding and for wrong lengths; wrong buffer sizes raise before the
+    C ABI is entered."""
+    A = tc
+    r = rng()
+    sk = A.SecretKey(int.from_bytes(r.bytes(40), "little"))
+    pk, sig = sk.public_key(), sk.sign(b"wire format")
+    assert len(pk.to_bytes()) == A.PK_SIZE and len(sig.to_bytes()) == A.SIG_SIZE
+    assert A.PublicKey.from_bytes(pk.to_bytes()) == pk and A.Signature.from_bytes(sig.to_bytes()) == sig
+    bad = bytearray(pk.to_bytes()); bad[47] ^= 1
+    with pytest.raises(A.FromBytesError):
+        A.PublicKey.from_bytes(bytes(bad))
+    with pytest.raises(A.FromBytesError):
+        A.Signature.from_bytes(b"\x00" * 95)
+    with pytest.raises(ValueError):
+        A.PublicKey(np.zeros(95, np.uint8))
+    with pytest.raises(ValueError):
+        A.engine().verify_g2_batch(pk.raw, sig.raw[:100], None, sig.raw)
+    with pytest.raises(ValueError):
+        A.engine().decrypt_batch(1, 1, np.zeros(64, np.uint8), np.zeros(96, np.uint8), [b"x"])
+    assert A.Commitment(np.zeros((0, 96), np.uint8)).evaluate(3)[0] == 0x40          # empty commitment -> G1::zero()

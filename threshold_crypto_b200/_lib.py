@@ -33,6 +33,12 @@ def _u8(a):
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
+def _need(name, arr, size):
+    """Every buffer length is checked before it crosses the C ABI (the library trusts its callers' sizes)."""
+    if arr is None or arr.size != size:
+        raise ValueError(f"{name}: expected {size} bytes, got {None if arr is None else arr.size}")
+
+
 def pack_msgs(msgs):
     """list of bytes -> (concatenated uint8 buffer, uint64 offsets[n+1])"""
     off = np.zeros(len(msgs) + 1, dtype=np.uint64)
@@ -101,6 +107,9 @@ class Engine:
     def verify_g2_batch(self, a_g1, b_g2, c_g1, d_g2):
         a, b, c, d = _u8(a_g1), _u8(b_g2), _u8(c_g1), _u8(d_g2)
         n = a.size // 96
+        _need("a_g1", a, 96 * n); _need("b_g2", b, 192 * n); _need("d_g2", d, 192 * n)
+        if c is not None:
+            _need("c_g1", c, 96 * n)
         ok = np.zeros(n, np.uint8)
         self._ck(self.lib.tcb_verify_g2_batch(self.ctx, C.c_size_t(n), _p(a), _p(b), _p(c), _p(d), _p(ok)))
         return ok
@@ -113,6 +122,7 @@ class Engine:
 
     def hash_g1_g2_batch(self, g1, msgs):
         g = _u8(g1)
+        _need("g1", g, 96 * len(msgs))
         buf, off = pack_msgs(msgs)
         out = np.zeros((len(msgs), 192), np.uint8)
         self._ck(self.lib.tcb_hash_g1_g2_batch(self.ctx, C.c_size_t(len(msgs)), _p(g), _p(buf), _p(off), _p(out)))
@@ -120,6 +130,7 @@ class Engine:
 
     def verify_batch(self, pk_g1, sig_g2, msgs):
         pk, sig = _u8(pk_g1), _u8(sig_g2)
+        _need("pk_g1", pk, 96 * len(msgs)); _need("sig_g2", sig, 192 * len(msgs))
         buf, off = pack_msgs(msgs)
         ok = np.zeros(len(msgs), np.uint8)
         self._ck(self.lib.tcb_verify_batch(self.ctx, C.c_size_t(len(msgs)), _p(pk), _p(sig), _p(buf), _p(off), _p(ok)))
@@ -127,6 +138,7 @@ class Engine:
 
     def sign_batch(self, sk, msgs):
         sk = _u8(sk)
+        _need("sk", sk, 32 * len(msgs))
         buf, off = pack_msgs(msgs)
         out = np.zeros((len(msgs), 192), np.uint8)
         self._ck(self.lib.tcb_sign_batch(self.ctx, C.c_size_t(len(msgs)), _p(sk), _p(buf), _p(off), _p(out)))
@@ -135,13 +147,14 @@ class Engine:
     def sign_g2_batch(self, sk, h_g2):
         sk, h = _u8(sk), _u8(h_g2)
         n = sk.size // 32
+        _need("sk", sk, 32 * n); _need("h_g2", h, 192 * n)
         out = np.zeros((n, 192), np.uint8)
         self._ck(self.lib.tcb_sign_g2_batch(self.ctx, C.c_size_t(n), _p(sk), _p(h), _p(out)))
         return out
 
     def combine_g2_batch(self, n, t, x_fr, shares_g2):
         x, s = _u8(x_fr), _u8(shares_g2)
-        assert x.size == n * (t + 1) * 32 and s.size == n * (t + 1) * 192
+        _need("x_fr", x, n * (t + 1) * 32); _need("shares_g2", s, n * (t + 1) * 192)
         out = np.zeros((n, 192), np.uint8)
         st = np.zeros(n, np.uint8)
         self._ck(self.lib.tcb_combine_g2_batch(self.ctx, C.c_size_t(n), C.c_size_t(t), _p(x), _p(s), _p(out), _p(st)))
@@ -149,7 +162,7 @@ class Engine:
 
     def combine_g1_batch(self, n, t, x_fr, shares_g1):
         x, s = _u8(x_fr), _u8(shares_g1)
-        assert x.size == n * (t + 1) * 32 and s.size == n * (t + 1) * 96
+        _need("x_fr", x, n * (t + 1) * 32); _need("shares_g1", s, n * (t + 1) * 96)
         out = np.zeros((n, 96), np.uint8)
         st = np.zeros(n, np.uint8)
         self._ck(self.lib.tcb_combine_g1_batch(self.ctx, C.c_size_t(n), C.c_size_t(t), _p(x), _p(s), _p(out), _p(st)))
@@ -158,12 +171,16 @@ class Engine:
     def decrypt_share_batch(self, sk, u_g1):
         sk, u = _u8(sk), _u8(u_g1)
         n = sk.size // 32
+        _need("sk", sk, 32 * n); _need("u_g1", u, 96 * n)
         out = np.zeros((n, 96), np.uint8)
         self._ck(self.lib.tcb_decrypt_share_batch(self.ctx, C.c_size_t(n), _p(sk), _p(u), _p(out)))
         return out
 
     def decrypt_batch(self, n, t, x_fr, shares_g1, vs):
         x, s = _u8(x_fr), _u8(shares_g1)
+        _need("x_fr", x, n * (t + 1) * 32); _need("shares_g1", s, n * (t + 1) * 96)
+        if len(vs) != n:
+            raise ValueError(f"decrypt_batch: {n} items but {len(vs)} ciphertext bodies")
         buf, off = pack_msgs(vs)
         out = np.zeros(buf.size, np.uint8)
         st = np.zeros(n, np.uint8)
@@ -172,8 +189,12 @@ class Engine:
 
     def commitment_eval_batch(self, coeff_g1, x_fr):
         c, x = _u8(coeff_g1), _u8(x_fr)
-        deg = c.size // 96 - 1
         n = x.size // 32
+        _need("x_fr", x, 32 * n)
+        if c.size == 0 or c.size % 96:
+            raise ValueError("commitment_eval_batch: the commitment must hold at least one 96-byte coefficient "
+                             "(the empty commitment evaluates to G1::zero(): api.Commitment handles it)")
+        deg = c.size // 96 - 1
         out = np.zeros((n, 96), np.uint8)
         self._ck(self.lib.tcb_commitment_eval_batch(self.ctx, C.c_size_t(deg), _p(c), C.c_size_t(n), _p(x), _p(out)))
         return out
@@ -187,14 +208,14 @@ class Engine:
 
     def g1_lincomb_batch(self, n, m, scalars, pts):
         sc, p = _u8(scalars), _u8(pts)
-        assert sc.size == n * m * 32 and p.size == n * m * 96
+        _need("scalars", sc, n * m * 32); _need("pts_g1", p, n * m * 96)
         out = np.zeros((n, 96), np.uint8)
         self._ck(self.lib.tcb_g1_lincomb_batch(self.ctx, C.c_size_t(n), C.c_size_t(m), _p(sc), _p(p), _p(out)))
         return out
 
     def g2_lincomb_batch(self, n, m, scalars, pts):
         sc, p = _u8(scalars), _u8(pts)
-        assert sc.size == n * m * 32 and p.size == n * m * 192
+        _need("scalars", sc, n * m * 32); _need("pts_g2", p, n * m * 192)
         out = np.zeros((n, 192), np.uint8)
         self._ck(self.lib.tcb_g2_lincomb_batch(self.ctx, C.c_size_t(n), C.c_size_t(m), _p(sc), _p(p), _p(out)))
         return out
@@ -203,6 +224,7 @@ class Engine:
         pk, r = _u8(pk_g1), _u8(r_fr)
         buf, off = pack_msgs(msgs)
         n = len(msgs)
+        _need("pk_g1", pk, 96 * n); _need("r_fr", r, 32 * n)
         u = np.zeros((n, 96), np.uint8); v = np.zeros(buf.size, np.uint8); w = np.zeros((n, 192), np.uint8)
         self._ck(self.lib.tcb_encrypt_batch(self.ctx, C.c_size_t(n), _p(pk), _p(r), _p(buf), _p(off), _p(u), _p(v), _p(w)))
         return u, [bytes(v[int(off[i]):int(off[i + 1])]) for i in range(n)], w
@@ -211,6 +233,7 @@ class Engine:
     def _codec(self, name, data, in_w, out_w, with_status):
         a = _u8(data)
         n = a.size // in_w
+        _need(name, a, in_w * n)
         out = np.zeros((n, out_w), np.uint8)
         if with_status:
             st = np.zeros(n, np.uint8)

@@ -59,13 +59,39 @@ def _frs(vals):
     return np.frombuffer(b"".join((int(v) % R).to_bytes(32, "little") for v in vals), np.uint8).copy()
 
 
+class FromBytesError(Error):
+    """src/error.rs:36-44 (FromBytesError::Invalid)"""
+
+
 class _Point:
-    SIZE = 0
+    """Holds the UNCOMPRESSED affine encoding the C ABI works on.  `raw` must come from the engine or from `from_bytes`
+    (the checked decoder): like the reference, where a PublicKey / Signature can only be built through a checked decode
+    (src/lib.rs:140-146, 246-252), the arithmetic assumes a point of the r-order subgroup."""
+    SIZE = 0          # uncompressed size
+    COMPRESSED = 0    # wire size (PK_SIZE / SIG_SIZE)
 
     def __init__(self, raw):
         raw = np.ascontiguousarray(raw, dtype=np.uint8).reshape(-1)
-        assert raw.size == self.SIZE
+        if raw.size != self.SIZE:
+            raise ValueError(f"{type(self).__name__}: expected {self.SIZE} bytes of uncompressed encoding, got {raw.size}")
         self.raw = raw
+
+    @classmethod
+    def from_bytes(cls, data):
+        """Checked decode of the compressed wire format (flags, x < p, on the curve, in the subgroup): src/lib.rs:140-146,246-252."""
+        data = np.frombuffer(bytes(data), np.uint8)
+        if data.size != cls.COMPRESSED:
+            raise FromBytesError(f"{cls.__name__}: expected {cls.COMPRESSED} bytes")
+        dec = engine().g1_decompress_batch if cls.COMPRESSED == PK_SIZE else engine().g2_decompress_batch
+        out, st = dec(data)
+        if st[0]:
+            raise FromBytesError(f"{cls.__name__}: invalid encoding")
+        return cls(out[0])
+
+    def to_bytes(self):
+        """Compressed wire format (src/lib.rs:149-153, 255-259)."""
+        comp = engine().g1_compress_batch if self.COMPRESSED == PK_SIZE else engine().g2_compress_batch
+        return comp(self.raw)[0].tobytes()
 
     def __eq__(self, o):
         return type(self) is type(o) and np.array_equal(self.raw, o.raw)
@@ -78,7 +104,7 @@ class _Point:
 
 
 class Signature(_Point):      # Signature(G2), src/lib.rs:202
-    SIZE = 192
+    SIZE, COMPRESSED = 192, SIG_SIZE
 
 
 class SignatureShare(Signature):   # src/lib.rs:266
@@ -86,11 +112,11 @@ class SignatureShare(Signature):   # src/lib.rs:266
 
 
 class DecryptionShare(_Point):     # DecryptionShare(G1), src/lib.rs:517
-    SIZE = 96
+    SIZE, COMPRESSED = 96, PK_SIZE
 
 
 class PublicKey(_Point):           # PublicKey(G1), src/lib.rs:79
-    SIZE = 96
+    SIZE, COMPRESSED = 96, PK_SIZE
 
     def verify_g2(self, sig, hash_g2_point):          # src/lib.rs:108-110
         return bool(engine().verify_g2_batch(self.raw, np.asarray(hash_g2_point, np.uint8), None, sig.raw)[0])
@@ -242,6 +268,10 @@ class Commitment:                  # poly::Commitment, src/poly.rs:429-433
         return self.evaluate_batch([i])[0]
 
     def evaluate_batch(self, idx):
+        idx = list(idx)
+        if self.coeff.shape[0] == 0:       # the empty commitment evaluates to G1::zero() (src/poly.rs:497-508)
+            inf = np.zeros(96, np.uint8); inf[0] = 0x40
+            return np.tile(inf, (len(idx), 1))
         return engine().commitment_eval_batch(self.coeff, _frs([into_fr(i) for i in idx]))
 
     def __add__(self, o):            # src/poly.rs:436-470: coefficient-wise G1 addition
@@ -273,7 +303,8 @@ def _powers(x, degree):             # src/poly.rs:729-738
 class BivarPoly:                    # poly::BivarPoly, src/poly.rs:513-650 (symmetric, Fr only: host side)
     def __init__(self, degree, coeff):
         self.degree, self.coeff = degree, [int(c) % R for c in coeff]
-        assert len(self.coeff) == coeff_pos(degree, degree) + 1
+        if len(self.coeff) != coeff_pos(degree, degree) + 1:
+            raise ValueError("BivarPoly: wrong number of coefficients for the degree")
 
     @staticmethod
     def random(degree, rng):
@@ -295,7 +326,8 @@ class BivarCommitment:              # poly::BivarCommitment, src/poly.rs:652-726
     def __init__(self, degree, coeff_g1):
         self.degree = degree
         self.coeff = np.ascontiguousarray(coeff_g1, dtype=np.uint8).reshape(-1, 96)
-        assert self.coeff.shape[0] == coeff_pos(degree, degree) + 1     # serde validation, src/serde_impl.rs:150-161
+        if self.coeff.shape[0] != coeff_pos(degree, degree) + 1:        # serde validation, src/serde_impl.rs:150-161
+            raise ValueError("BivarCommitment: wrong number of coefficients for the degree")
 
     def evaluate(self, x, y):        # src/poly.rs:693-709
         d = self.degree

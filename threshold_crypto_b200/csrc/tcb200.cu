@@ -584,7 +584,7 @@ extern "C" int tcb_sign_g2_batch(tcb_ctx *ctx, size_t n, const u8 *sk, const u8 
     return sign_common(ctx, n, sk, nullptr, nullptr, h, out);
 }
 extern "C" int tcb_combine_g2_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
-    HOST_PROLOGUE_G(4096)
+    HOST_PROLOGUE_G(16384)
     size_t m = t + 1;
     FOR_EACH_DEV
         u8 *dx = up(ctx, d, x + 32 * m * s.lo, 32 * m * cnt), *dsh = up(ctx, d, shares + 192 * m * s.lo, 192 * m * cnt);
@@ -596,7 +596,7 @@ extern "C" int tcb_combine_g2_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *
     return sync_all(ctx);
 }
 extern "C" int tcb_combine_g1_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
-    HOST_PROLOGUE_G(2048)
+    HOST_PROLOGUE_G(8192)
     size_t m = t + 1;
     FOR_EACH_DEV
         u8 *dx = up(ctx, d, x + 32 * m * s.lo, 32 * m * cnt), *dsh = up(ctx, d, shares + 96 * m * s.lo, 96 * m * cnt);
@@ -609,7 +609,7 @@ extern "C" int tcb_combine_g1_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *
 }
 extern "C" int tcb_decrypt_batch(tcb_ctx *ctx, size_t n, size_t t, const u8 *x, const u8 *shares, const u8 *v, const u64 *voff,
                                  u8 *out, u8 *status) {
-    HOST_PROLOGUE_G(1024)
+    HOST_PROLOGUE_G(8192)
     size_t m = t + 1;
     std::vector<std::vector<u64>> keep;
     keep.reserve(pieces.size());
@@ -659,7 +659,7 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *ctx, size_t deg, const u8 *coe
 // ---- out_i = sum_k s_{i,k} P_{i,k}  (BivarCommitment::row / evaluate, src/poly.rs:693-726:
 // the caller supplies the Fr power products as scalars).  Same per-term + sum kernels as interpolate.
 static int lincomb_common(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out, int g2) {
-    HOST_PROLOGUE_G(2048)
+    HOST_PROLOGUE_G(8192)
     size_t pw = g2 ? 192 : 96;
     if (m == 0) { if (ctx) ctx->err = "m must be >= 1"; return -2; }
     std::vector<u8> hstatus(n, 0);

@@ -329,10 +329,18 @@ class ShardedEngine:
         ph = _Phases(self.cuda)
         d_x = None
         d_c = torch.empty(96 * (deg + 1), dtype=torch.uint8, device=self.dev)
+        # The cost of a point grows with the bit length of x (Horner skips leading zeros) and callers pass increasing indices
+        # (public_key_share(i) -> x = i + 1), so contiguous slices would leave the last rank with the most expensive points: the
+        # points are dealt round-robin instead (rank r gets i = r, r + world, ...), a host-side permutation of 32 B per point.
+        perm = np.concatenate([np.arange(r, n, self.world) for r in range(self.world)]) if self.world > 1 else None
         if self._is_root():
             coeff_g1, x_fr = np.ascontiguousarray(coeff_g1, np.uint8).reshape(-1), np.ascontiguousarray(x_fr, np.uint8).reshape(-1)
             if coeff_g1.size != 96 * (deg + 1) or x_fr.size != 32 * n:
                 raise ValueError("commitment_eval: array sizes do not match n and deg")
+            if perm is not None:
+                x_fr = torch.from_numpy(x_fr.reshape(n, 32)[perm].reshape(-1))
+                if self.cuda:
+                    x_fr = x_fr.pin_memory()
             d_c, d_x = self._to_dev(coeff_g1), self._to_dev(x_fr)
         ph.mark("h2d")
         self._bcast(d_c)
@@ -349,7 +357,13 @@ class ShardedEngine:
         ph.mark("compute")
         (full,) = self._gather([(out, 96)], n)
         ph.mark("gather")
-        res = self._host(full).reshape(n, 96) if self._is_root() else None
+        res = None
+        if self._is_root():
+            res = self._host(full).reshape(n, 96)
+            if perm is not None:
+                unperm = np.empty_like(res)
+                unperm[perm] = res
+                res = unperm
         ph.mark("d2h")
         self.last_timing = ph.result()
         return res
