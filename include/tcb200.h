@@ -104,6 +104,13 @@ int tcb_g1_mul_gen_batch(tcb_ctx *, size_t n, const uint8_t *sk, uint8_t *out_g1
 int tcb_g1_lincomb_batch(tcb_ctx *, size_t n, size_t m, const uint8_t *scalars_fr, const uint8_t *pts_g1, uint8_t *out_g1);
 int tcb_g2_lincomb_batch(tcb_ctx *, size_t n, size_t m, const uint8_t *scalars_fr, const uint8_t *pts_g2, uint8_t *out_g2);
 
+/* SURVEY §8(f) row 4 — Fr-side Poly algebra on canonical little-endian Fr coefficients (32 B each, constant term first).
+ * Poly::evaluate (src/poly.rs:358-369) of ONE polynomial of degree deg at n points, and the product of n pairs of polynomials of
+ * degrees da and db (impl Mul for Poly, src/poly.rs:173-194; out holds da + db + 1 coefficients per item, no zero trimming).
+ * rc -10 = a scalar >= r. */
+int tcb_poly_eval_batch(tcb_ctx *, size_t deg, const uint8_t *coeff_fr, size_t n, const uint8_t *x_fr, uint8_t *out_fr);
+int tcb_poly_mul_batch(tcb_ctx *, size_t n, size_t da, const uint8_t *a_fr, size_t db, const uint8_t *b_fr, uint8_t *out_fr);
+
 /* SURVEY §8(f) row 2 — PublicKey::encrypt_with_rng (src/lib.rs:128-137) with the random scalars r
  * drawn by the caller (Fr::random stays in the Rust shim): u = g1*r, v = xor_with_hash(pk*r, msg),
  * w = hash_g1_g2(u, v)*r.  v_out has the layout of msgs (same offsets). */

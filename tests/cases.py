@@ -113,6 +113,29 @@ def check_all(E, O, n_sig=6, n_comb=3, t=3, deg=6, n_eval=5, seed=7):
     assert np.array_equal(out, O.g1_mul_gen_batch(O.poly_eval(coeff, xs)))
 
 
+def check_poly(E, O, seed=13):
+    """SURVEY §8(f) row 4: Poly::evaluate and Poly * Poly in Fr against the oracle's Horner / Python integers, incl. the
+    reference's own known-answer polynomial (src/poly.rs:783-797: 5 x^3 + x - 2 and x^3 + 1... evaluated at small points)."""
+    rng = np.random.default_rng(seed)
+    coeff = rand_fr(rng, 9)
+    xs = fr_bytes([0, 1, 2, R - 1, 65536] + [int.from_bytes(rng.bytes(40), "little") for _ in range(8)])
+    assert np.array_equal(E.poly_eval_batch(coeff, xs), O.poly_eval(coeff, xs))
+    kat = fr_bytes([R - 2, 1, 0, 5])                      # 5 x^3 + x - 2  (poly.rs:786)
+    got = E.poly_eval_batch(kat, fr_bytes([1, 2, 3]))
+    assert [int.from_bytes(bytes(g), "little") for g in got] == [4, 40, 136]
+    n, da, db = 3, 4, 2
+    a = [[int.from_bytes(rng.bytes(40), "little") % R for _ in range(da + 1)] for _ in range(n)]
+    b = [[int.from_bytes(rng.bytes(40), "little") % R for _ in range(db + 1)] for _ in range(n)]
+    a[1][da] = 0; b[2] = [0] * (db + 1)                   # a leading zero and a zero polynomial
+    out = E.poly_mul_batch(n, fr_bytes([c for r_ in a for c in r_]), fr_bytes([c for r_ in b for c in r_]))
+    for i in range(n):
+        exp = [0] * (da + db + 1)
+        for p_, ca in enumerate(a[i]):
+            for q_, cb in enumerate(b[i]):
+                exp[p_ + q_] = (exp[p_ + q_] + ca * cb) % R
+        assert [int.from_bytes(bytes(c), "little") for c in out[i]] == exp
+
+
 def check_edges(E, O):
     """Edge semantics of SURVEY §7: infinity operands, t == 0, duplicate indices, zero scalars,
     empty batches, ragged messages."""

@@ -137,6 +137,21 @@ extern "C" int tcb_commitment_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff,
     return 0;
 }
 
+extern "C" int tcb_poly_eval_batch(tcb_ctx *, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
+    std::vector<Fr> cm(deg + 1);
+    u8 bad = 0;
+    for (size_t c = 0; c <= deg; c++) task_fr_to_mont(c, coeff, cm.data(), &bad);
+    for (size_t i = 0; i < n; i++) task_poly_eval(i, deg, cm.data(), x, out, &bad);
+    return bad ? -10 : 0;
+}
+extern "C" int tcb_poly_mul_batch(tcb_ctx *, size_t n, size_t da, const u8 *a, size_t db, const u8 *b, u8 *out) {
+    std::vector<Fr> am(n * (da + 1)), bm(n * (db + 1));
+    u8 bad = 0;
+    for (size_t i = 0; i < am.size(); i++) task_fr_to_mont(i, a, am.data(), &bad);
+    for (size_t i = 0; i < bm.size(); i++) task_fr_to_mont(i, b, bm.data(), &bad);
+    for (size_t u = 0; u < n * (da + db + 1); u++) task_poly_mul(u, da, db, am.data(), bm.data(), out);
+    return bad ? -10 : 0;
+}
 extern "C" int tcb_g1_lincomb_batch(tcb_ctx *, size_t n, size_t m, const u8 *sc, const u8 *pts, u8 *out) {
     size_t G = g_groups < m ? g_groups : m;
     std::vector<Jac1Store> terms(n * G);

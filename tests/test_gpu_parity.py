@@ -363,3 +363,15 @@ def test_config5_commit_eval_full_size(gpu_engine, O):
     assert np.array_equal(out2, E.g1_mul_gen_batch(fr_bytes(_poly_shares(coeff, xr_int))))
     assert np.array_equal(out2[:16], O.commitment_eval_batch(comm, xr[:16 * 32]))
     O.set_threads(1)
+
+
+def test_fr_poly_algebra(gpu_engine, O):
+    """SURVEY §8(f) row 4 on the device: Poly::evaluate / Poly * Poly kernels against the oracle and Python integers, and a
+    degree-1023 polynomial at 2^14 points against the oracle's Horner."""
+    cases.check_poly(gpu_engine, O)
+    rng = np.random.default_rng(66)
+    coeff = rand_fr(rng, 1024)
+    xs = rand_fr(rng, 1 << 14)
+    O.set_threads(16)
+    assert np.array_equal(gpu_engine.poly_eval_batch(coeff, xs), O.poly_eval(coeff, xs))
+    O.set_threads(1)

@@ -115,3 +115,7 @@ def test_commit_eval_split_blocks(emu, O):
             assert np.array_equal(emu.commitment_eval_batch(comm, xs), exp), B
     finally:
         emu.set_eval_split(0)
+
+
+def test_hostemu_poly_algebra(emu, O):
+    cases.check_poly(emu, O)

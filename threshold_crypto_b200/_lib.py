@@ -220,6 +220,27 @@ class Engine:
         self._ck(self.lib.tcb_g2_lincomb_batch(self.ctx, C.c_size_t(n), C.c_size_t(m), _p(sc), _p(p), _p(out)))
         return out
 
+    # ---- Fr-side Poly algebra
+    def poly_eval_batch(self, coeff_fr, x_fr):
+        """Poly::evaluate of one polynomial (canonical LE coefficients, constant term first) at every x"""
+        c, x = _u8(coeff_fr), _u8(x_fr)
+        if c.size == 0 or c.size % 32 or x.size % 32:
+            raise ValueError("poly_eval_batch: coefficients and points are 32-byte scalars, at least one coefficient")
+        n = x.size // 32
+        out = np.zeros((n, 32), np.uint8)
+        self._ck(self.lib.tcb_poly_eval_batch(self.ctx, C.c_size_t(c.size // 32 - 1), _p(c), C.c_size_t(n), _p(x), _p(out)))
+        return out
+
+    def poly_mul_batch(self, n, a_fr, b_fr):
+        """n products of a polynomial of degree da with one of degree db -> (n, da + db + 1, 32)"""
+        a, b = _u8(a_fr), _u8(b_fr)
+        if n == 0 or a.size % (32 * n) or b.size % (32 * n) or a.size == 0 or b.size == 0:
+            raise ValueError("poly_mul_batch: n items of (da + 1) and (db + 1) 32-byte coefficients")
+        da, db = a.size // (32 * n) - 1, b.size // (32 * n) - 1
+        out = np.zeros((n, da + db + 1, 32), np.uint8)
+        self._ck(self.lib.tcb_poly_mul_batch(self.ctx, C.c_size_t(n), C.c_size_t(da), _p(a), C.c_size_t(db), _p(b), _p(out)))
+        return out
+
     def encrypt_batch(self, pk_g1, r_fr, msgs):
         pk, r = _u8(pk_g1), _u8(r_fr)
         buf, off = pack_msgs(msgs)

@@ -205,6 +205,18 @@ class Poly:                        # poly::Poly, src/poly.rs:40-44 (Fr algebra s
             acc = (acc * x + c) % R
         return acc
 
+    def evaluate_batch(self, idx):                     # Poly::evaluate at many points in one GPU call (Fr Horner per thread)
+        if not self.coeff:
+            return [0] * len(list(idx))
+        out = engine().poly_eval_batch(_frs(self.coeff), _frs([into_fr(i) for i in idx]))
+        return [int.from_bytes(bytes(o), "little") for o in out]
+
+    def mul_gpu(self, o):                              # impl Mul for Poly (src/poly.rs:173-194) on the GPU
+        if not self.coeff or not o.coeff:
+            return Poly([])
+        out = engine().poly_mul_batch(1, _frs(self.coeff), _frs(o.coeff))[0]
+        return Poly([int.from_bytes(bytes(c), "little") for c in out])._trim()
+
     def commitment(self):                              # src/poly.rs:372-377: g1 * c_k on the GPU
         return Commitment(engine().g1_mul_gen_batch(_frs(self.coeff)))
 

@@ -82,6 +82,19 @@ __global__ void __launch_bounds__(128, 4) k_commit_eval_part(size_t units, size_
     if (u < units) task_commit_eval_part(u, B, L, deg, coeff, x, out);
 }
 
+__global__ void __launch_bounds__(128) k_fr_to_mont(size_t n, const u8 *in, Fr *out, u8 *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_fr_to_mont(i, in, out, bad);
+}
+__global__ void __launch_bounds__(128) k_poly_eval(size_t n, size_t deg, const Fr *cm, const u8 *x, u8 *out, u8 *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_poly_eval(i, deg, cm, x, out, bad);
+}
+__global__ void __launch_bounds__(128) k_poly_mul(size_t units, size_t da, size_t db, const Fr *am, const Fr *bm, u8 *out) {
+    size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < units) task_poly_mul(u, da, db, am, bm, out);
+}
+
 static __device__ __forceinline__ u64 splitmix(u64 &s) {
     u64 z = (s += 0x9e3779b97f4a7c15ULL);
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
@@ -211,6 +224,15 @@ size_t commit_eval_units_per_sm() {
 }
 void run_commit_eval_part(cudaStream_t st, size_t n, size_t B, size_t L, size_t deg, const void *tab, const u8 *x, void *terms) {
     if (n * B) k_commit_eval_part<<<grid1(n * B), 128, 0, st>>>(n * B, B, L, deg, (const Aff1Store *)tab, x, (Jac1Store *)terms);
+}
+size_t fr_bytes() { return sizeof(Fr); }
+void run_fr_to_mont(cudaStream_t st, size_t n, const u8 *in, void *out, u8 *bad) { if (n) k_fr_to_mont<<<grid1(n), 128, 0, st>>>(n, in, (Fr *)out, bad); }
+void run_poly_eval(cudaStream_t st, size_t n, size_t deg, const void *cm, const u8 *x, u8 *out, u8 *bad) {
+    if (n) k_poly_eval<<<grid1(n), 128, 0, st>>>(n, deg, (const Fr *)cm, x, out, bad);
+}
+void run_poly_mul(cudaStream_t st, size_t n, size_t da, size_t db, const void *am, const void *bm, u8 *out) {
+    size_t units = n * (da + db + 1);
+    if (units) k_poly_mul<<<grid1(units), 128, 0, st>>>(units, da, db, (const Fr *)am, (const Fr *)bm, out);
 }
 void run_encrypt_uv(cudaStream_t st, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out) {
     if (n) k_encrypt_uv<<<grid1(n), 128, 0, st>>>(n, pk, r, msgs, off, u_out, v_out);

@@ -20,7 +20,10 @@ __global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_verify_g2_quad(size_t n,
 }
 // Final exponentiation + "== 1" of the Miller-loop values produced by k_miller_quad (k_miller.cu) or k_miller_quad_reg:
 // f of item i, lane l, coefficient k at fin[(4 i + l) * 3 + k]  (576 B per item through HBM/L2).
-__global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_final_exp_quad(size_t n, const Fp *fin, const u8 *enc_ok, u8 *ok) {
+#ifndef TCB_FE_MINB
+#define TCB_FE_MINB TCB_QUAD_MINB
+#endif
+__global__ void __launch_bounds__(128, TCB_FE_MINB) k_final_exp_quad(size_t n, const Fp *fin, const u8 *enc_ok, u8 *ok) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     bool live = i < n;
     if (!live) i = n - 1;

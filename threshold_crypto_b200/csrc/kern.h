@@ -69,6 +69,10 @@ void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);
 size_t commit_eval_units_per_sm();
 void run_commit_eval_part(cudaStream_t st, size_t n, size_t B, size_t L, size_t deg, const void *tab, const u8 *x, void *terms);   // then run_g1_sum(n, B, ...)
+size_t fr_bytes();
+void run_fr_to_mont(cudaStream_t st, size_t n, const u8 *in, void *out, u8 *bad);
+void run_poly_eval(cudaStream_t st, size_t n, size_t deg, const void *cm, const u8 *x, u8 *out, u8 *bad);
+void run_poly_mul(cudaStream_t st, size_t n, size_t da, size_t db, const void *am, const void *bm, u8 *out);
 void run_encrypt_uv(cudaStream_t st, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off, u8 *u_out, u8 *v_out);
 void run_g1_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out);
 void run_g1_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status);

@@ -439,6 +439,37 @@ TCB_HD void lagrange_finish_item(LagrangeND *nd, size_t m, u32 *out) {
     }
 }
 
+// ----------------------------------------------------------------------------- §8(f) row 4: Fr-side Poly algebra
+// Poly::evaluate (src/poly.rs:358-369: Horner from the leading coefficient) and Poly * Poly (src/poly.rs:173-194: schoolbook
+// convolution) on canonical little-endian Fr coefficients; `cm` / `am` / `bm` are the coefficients already in Montgomery form
+// (k_fr_to_mont), outputs are canonical again.
+TCB_HD void task_fr_to_mont(size_t i, const u8 *in, Fr *out, u8 *bad) {
+    bool ok = true;
+    out[i] = fr_load_le(in + 32 * i, ok);
+    if (!ok) *bad = 3;
+}
+TCB_HD void fr_store_le(u8 *b, const Fr &a) {
+    Fr c = from_mont<FrParams>(a);
+    for (int i = 0; i < 8; i++) { b[4 * i] = (u8)c.l[i]; b[4 * i + 1] = (u8)(c.l[i] >> 8); b[4 * i + 2] = (u8)(c.l[i] >> 16); b[4 * i + 3] = (u8)(c.l[i] >> 24); }
+}
+TCB_HD void task_poly_eval(size_t i, size_t deg, const Fr *cm, const u8 *x_fr, u8 *out_fr, u8 *bad) {
+    bool ok = true;
+    Fr x = fr_load_le(x_fr + 32 * i, ok);
+    Fr acc = cm[deg];
+    for (size_t c = deg; c-- > 0;) acc = acc * x + cm[c];
+    fr_store_le(out_fr + 32 * i, acc);
+    if (!ok) *bad = 3;
+}
+// out_{item,k} = sum_i a_{item,i} * b_{item,k-i}
+TCB_HD void task_poly_mul(size_t u, size_t da, size_t db, const Fr *am, const Fr *bm, u8 *out_fr) {
+    size_t w = da + db + 1, item = u / w, k = u % w;
+    const Fr *a = am + item * (da + 1), *b = bm + item * (db + 1);
+    size_t lo = k > db ? k - db : 0, hi = k < da ? k : da;
+    Fr acc = Fr::zero();
+    for (size_t i = lo; i <= hi; i++) acc = acc + a[i] * b[k - i];
+    fr_store_le(out_fr + 32 * u, acc);
+}
+
 // ----------------------------------------------------------------------------- per-item tasks
 // a1: e(a,b) == e(c,d); c == nullptr means the G1 generator (src/lib.rs:108-110,182-186,508-512)
 template <class F2>

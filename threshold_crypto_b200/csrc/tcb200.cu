@@ -682,6 +682,45 @@ static int lincomb_common(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, c
 extern "C" int tcb_g1_lincomb_batch(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out) { return lincomb_common(ctx, n, m, scalars, pts, out, 0); }
 extern "C" int tcb_g2_lincomb_batch(tcb_ctx *ctx, size_t n, size_t m, const u8 *scalars, const u8 *pts, u8 *out) { return lincomb_common(ctx, n, m, scalars, pts, out, 1); }
 
+// ---- Fr-side Poly algebra (src/poly.rs:173-194, 358-369)
+extern "C" int tcb_poly_eval_batch(tcb_ctx *ctx, size_t deg, const u8 *coeff, size_t n, const u8 *x, u8 *out) {
+    HOST_PROLOGUE
+    std::vector<u8> bad(pieces.size() + 1, 0);
+    size_t pi = 0;
+    FOR_EACH_DEV
+        u8 *dc = up(ctx, d, coeff, 32 * (deg + 1)), *dx = up(ctx, d, x + 32 * s.lo, 32 * cnt);
+        void *cm = arena_alloc(ctx, d, (deg + 1) * fr_bytes());
+        u8 *dout = (u8 *)arena_alloc(ctx, d, 32 * cnt), *dbad = (u8 *)arena_alloc(ctx, d, 4);
+        if (!dc || !dx || !cm || !dout || !dbad) return -1;
+        CK(cudaMemsetAsync(dbad, 0, 4, st));
+        RUN(run_fr_to_mont(st, deg + 1, dc, cm, dbad));
+        RUN(run_poly_eval(st, cnt, deg, cm, dx, dout, dbad));
+        if (down(ctx, d, out + 32 * s.lo, dout, 32 * cnt) || down(ctx, d, &bad[pi++], dbad, 1)) return -1;
+    END_FOR_EACH_DEV
+    if (sync_all(ctx)) return -1;
+    for (u8 b : bad) if (b) { ctx->err = "poly_eval: a scalar is not a canonical Fr (>= r)"; return -10; }
+    return 0;
+}
+extern "C" int tcb_poly_mul_batch(tcb_ctx *ctx, size_t n, size_t da, const u8 *a, size_t db, const u8 *b, u8 *out) {
+    HOST_PROLOGUE
+    std::vector<u8> bad(pieces.size() + 1, 0);
+    size_t pi = 0, w = da + db + 1;
+    FOR_EACH_DEV
+        u8 *da_ = up(ctx, d, a + 32 * (da + 1) * s.lo, 32 * (da + 1) * cnt), *db_ = up(ctx, d, b + 32 * (db + 1) * s.lo, 32 * (db + 1) * cnt);
+        void *am = arena_alloc(ctx, d, (da + 1) * cnt * fr_bytes()), *bm = arena_alloc(ctx, d, (db + 1) * cnt * fr_bytes());
+        u8 *dout = (u8 *)arena_alloc(ctx, d, 32 * w * cnt), *dbad = (u8 *)arena_alloc(ctx, d, 4);
+        if (!da_ || !db_ || !am || !bm || !dout || !dbad) return -1;
+        CK(cudaMemsetAsync(dbad, 0, 4, st));
+        RUN(run_fr_to_mont(st, (da + 1) * cnt, da_, am, dbad));
+        RUN(run_fr_to_mont(st, (db + 1) * cnt, db_, bm, dbad));
+        RUN(run_poly_mul(st, cnt, da, db, am, bm, dout));
+        if (down(ctx, d, out + 32 * w * s.lo, dout, 32 * w * cnt) || down(ctx, d, &bad[pi++], dbad, 1)) return -1;
+    END_FOR_EACH_DEV
+    if (sync_all(ctx)) return -1;
+    for (u8 x : bad) if (x) { ctx->err = "poly_mul: a coefficient is not a canonical Fr (>= r)"; return -10; }
+    return 0;
+}
+
 // ---- PublicKey::encrypt_with_rng with caller-supplied r (src/lib.rs:128-137)
 extern "C" int tcb_encrypt_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 *r, const u8 *msgs, const u64 *off,
                                  u8 *u_out, u8 *v_out, u8 *w_out) {
