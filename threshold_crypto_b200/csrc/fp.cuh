@@ -163,7 +163,10 @@ TCB_HD Mont<P> mneg(const Mont<P> &a) {
     return r;
 }
 
-// --- CIOS building blocks on split even/odd accumulators (see DESIGN.md "Fp multiply")
+// --- CIOS building blocks on split even/odd accumulators (see DESIGN.md "Fp multiply").
+// Credit: this formulation of the row (mul_n / cmad_n / madc_n_rshift / mad_row_redc, the a+1 views, the even/odd role swap
+// that makes the per-row shift free) follows Supranational's sppark, ff/mont_t.cuh (Apache-2.0), as recalled from its public
+// source; dot2 and the K-term dot_rows4 / dot_finish below are additions of this repository.
 template <int N>
 TCB_HD void mul_n(u32 *acc, const u32 *a, u32 bi) {
 #pragma unroll
