@@ -17,6 +17,7 @@ DEFAULT_LIB = os.environ.get("TCB200_LIB") or os.path.join(_HERE, "csrc", "libtc
 
 ENGINE_QUAD_REG = 1      # round-1 fused register-engine pairing kernel (self-test reference, A/B measurement)
 ENGINE_QUAD_SMEM = 2     # default: shared-memory Miller loop + final-exponentiation kernel
+ENGINE_QUAD_SMEM_FE = 3  # as 2 with the final exponentiation's products / squarings on shared-memory cells too (measurement)
 
 
 class TcbError(RuntimeError):

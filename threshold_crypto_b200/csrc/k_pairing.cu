@@ -4,6 +4,7 @@
 #endif
 #include "kern.h"
 #include "quad.cuh"
+#include "quadsm.cuh"
 using namespace tcb;
 
 // one item per QUAD of lanes (quad.cuh); h_g2 replaces b_g2 when the hash was computed on device
@@ -23,14 +24,133 @@ __global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_verify_g2_quad(size_t n,
 #ifndef TCB_FE_MINB
 #define TCB_FE_MINB TCB_QUAD_MINB
 #endif
-__global__ void __launch_bounds__(128, TCB_FE_MINB) k_final_exp_quad(size_t n, const Fp *fin, const u8 *enc_ok, u8 *ok) {
+__global__ void __launch_bounds__(128, TCB_FE_MINB) k_final_exp_quad(size_t n, const Fp *fin, const u8 *enc_ok, u8 *ok, Fp *fe_out) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     bool live = i < n;
     if (!live) i = n - 1;
     const Fp *p = fin + (i * 4 + (threadIdx.x & 3u)) * 3;
     Fp12Q f;
     f.h.c0.h = ldg_fp(p); f.h.c1.h = ldg_fp(p + 1); f.h.c2.h = ldg_fp(p + 2);
-    bool res = fp12_is_one(final_exponentiation(fp12_conj(f)));
+    Fp12Q g = final_exponentiation(fp12_conj(f));
+    bool res = fp12_is_one(g);
+    if (live && fe_out) { Fp *o = fe_out + (i * 4 + (threadIdx.x & 3u)) * 3; stg_fp(o, g.h.c0.h); stg_fp(o + 1, g.h.c1.h); stg_fp(o + 2, g.h.c2.h); }
+    if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok[i]) ? 1 : 0;
+}
+// ---- final exponentiation with its Fp12 products and compressed squarings on shared-memory cells (quadsm.cuh: qf_mul12,
+// qf_comp_sqr); the cold pieces (inversion, Frobenius maps, decompression of the saved powers, the first cyclotomic squaring)
+// stay on the register engine and move values through the cells' own columns.
+TCB_D Fp12Q qf_ld12(u32 v) {
+    Fp12Q r;
+    u32 t = q_tid();
+    r.h.c0.h = q_ld(v, t); r.h.c1.h = q_ld(v + 1, t); r.h.c2.h = q_ld(v + 2, t);
+    return r;
+}
+TCB_D void qf_st12(u32 v, const Fp12Q &a) {      // the caller hands off with __syncwarp()
+    q_st(v, a.h.c0.h); q_st(v + 1, a.h.c1.h); q_st(v + 2, a.h.c2.h);
+}
+// V[dst] <- conj(V[src]^x): compressed chain on cells, decompression + product of the saved powers on the register engine
+static __device__ __noinline__ void qf_exp_by_x(u32 dst, u32 src, u64 x) {
+    const u32 t = q_tid();
+    const bool p0 = q_pair() == 0;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    {
+        Fp a = q_ld(src + (p0 ? 1u : 0u), t), b = q_ld(src + 2, t);
+        __syncwarp();
+        q_st(QF_CA, a); q_st(QF_CB, b);
+        __syncwarp();
+    }
+    CompQ saved[COMP_MAX];
+    int ns = 0, want = 0;
+#pragma unroll 1
+    for (int i = 1; i <= top; i++) {
+        qf_comp_sqr();
+        if ((x >> i) & 1) {
+            want++;
+            if (ns < COMP_MAX) { saved[ns].a.h = q_ld(QF_CA, t); saved[ns].b.h = q_ld(QF_CB, t); ns++; }
+        }
+    }
+    Fp12Q acc;
+    if (want != ns || ns == 0 || !comp_decompress_product(saved, ns, acc)) acc = fp12_conj(fp12_exp_by_x_plain(qf_ld12(src), x));   // conj twice = id below
+    else if (x & 1) acc = fp12_mul(acc, qf_ld12(src));
+    acc = fp12_conj(acc);
+    __syncwarp();
+    qf_st12(dst, acc);
+    __syncwarp();
+}
+TCB_D void qf_conj_inplace(u32 v) {              // own cells only
+    if (q_pair()) { u32 t = q_tid(); for (u32 k = 0; k < 3; k++) q_st(v + k, -q_ld(v + k, t)); }
+    __syncwarp();
+}
+// same chain as quad.cuh final_exponentiation; returns the result in registers
+static __device__ __noinline__ Fp12Q qf_final_exponentiation(const Fp12Q &in) {
+    const u64 x = TCB_BLS_X;
+    // easy part: r = (conj(in) * in^-1)^(p^2 + 1)
+    qf_st12(QF_V0, fp12_conj(in));
+    qf_st12(QF_V1, fp12_inv(in));
+    __syncwarp();
+    qf_mul12(QF_V0, QF_V0, QF_V1);
+    Fp12Q f2 = qf_ld12(QF_V0);
+    __syncwarp();
+    qf_st12(QF_V1, f2);
+    qf_st12(QF_V0, fp12_frob(f2, 2));
+    __syncwarp();
+    qf_mul12(QF_V0, QF_V0, QF_V1);                 // V0 = r
+    Fp12Q r = qf_ld12(QF_V0);
+    Fp12Q y0 = fp12_cyclo_sqr(r);
+    __syncwarp();
+    qf_st12(QF_V1, y0);
+    __syncwarp();
+    qf_exp_by_x(QF_V2, QF_V1, x);                  // y1
+    qf_exp_by_x(QF_V3, QF_V2, x >> 1);             // y2
+    qf_st12(QF_V1, fp12_conj(r));                  // y3 = conj(r)   (y0 and r are kept in registers / the local frame)
+    __syncwarp();
+    qf_mul12(QF_V2, QF_V2, QF_V1);                 // y1 = y1 * y3
+    qf_conj_inplace(QF_V2);
+    qf_mul12(QF_V2, QF_V2, QF_V3);                 // y1 = conj(y1) * y2
+    qf_exp_by_x(QF_V3, QF_V2, x);                  // y2 = y1^x
+    qf_exp_by_x(QF_V1, QF_V3, x);                  // y3 = y2^x
+    qf_conj_inplace(QF_V2);                        // y1 = conj(y1)
+    qf_mul12(QF_V1, QF_V1, QF_V2);                 // y3 = y3 * y1
+    qf_conj_inplace(QF_V2);                        // y1 = conj(y1)
+    {
+        Fp12Q y1 = fp12_frob(qf_ld12(QF_V2), 3), y2 = fp12_frob(qf_ld12(QF_V3), 2);
+        __syncwarp();
+        qf_st12(QF_V2, y1); qf_st12(QF_V3, y2);
+        __syncwarp();
+    }
+    qf_mul12(QF_V2, QF_V2, QF_V3);                 // y1 = y1 * y2
+    qf_exp_by_x(QF_V3, QF_V1, x);                  // y2 = y3^x
+    qf_st12(QF_V0, y0);
+    __syncwarp();
+    qf_mul12(QF_V3, QF_V3, QF_V0);                 // y2 = y2 * y0
+    qf_st12(QF_V0, r);
+    __syncwarp();
+    qf_mul12(QF_V3, QF_V3, QF_V0);                 // y2 = y2 * r
+    qf_mul12(QF_V2, QF_V2, QF_V3);                 // y1 = y1 * y2
+    {
+        Fp12Q y2 = fp12_frob(qf_ld12(QF_V1), 1);   // y2 = frob(y3)
+        __syncwarp();
+        qf_st12(QF_V3, y2);
+        __syncwarp();
+    }
+    qf_mul12(QF_V2, QF_V2, QF_V3);
+    return qf_ld12(QF_V2);
+}
+#ifndef TCB_FESM_MINB
+#define TCB_FESM_MINB 2
+#endif
+// fe_out (optional, self-test): the value of the final exponentiation in the layout of fin
+__global__ void __launch_bounds__(QNT, TCB_FESM_MINB) k_final_exp_sm(size_t n, const Fp *fin, const u8 *enc_ok, u8 *ok, Fp *fe_out) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    bool live = i < n;
+    if (!live) i = n - 1;
+    const Fp *p = fin + (i * 4 + (threadIdx.x & 3u)) * 3;
+    Fp12Q f;
+    f.h.c0.h = ldg_fp(p); f.h.c1.h = ldg_fp(p + 1); f.h.c2.h = ldg_fp(p + 2);
+    Fp12Q g = qf_final_exponentiation(fp12_conj(f));
+    bool res = fp12_is_one(g);
+    if (live && fe_out) { Fp *o = fe_out + (i * 4 + (threadIdx.x & 3u)) * 3; stg_fp(o, g.h.c0.h); stg_fp(o + 1, g.h.c1.h); stg_fp(o + 2, g.h.c2.h); }
     if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok[i]) ? 1 : 0;
 }
 // the register engine's Miller loop alone, same output format (self-test reference for the shared-memory engine)
@@ -208,6 +328,7 @@ cudaError_t upload_consts_pairing(const Consts &c) {
     // the pairing kernel keeps its small call frames in L1: no shared-memory carve-out
     cudaFuncSetAttribute(k_verify_g2_quad, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_final_exp_quad, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    if (cudaFuncSetAttribute(k_final_exp_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES) != cudaSuccess) return cudaErrorInvalidValue;
     cudaFuncSetAttribute(k_miller_quad_reg, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     return cudaMemcpyToSymbol(d_consts, &c, sizeof c);
 }
@@ -216,9 +337,13 @@ void run_verify_g2_quad(cudaStream_t st, size_t n, const u8 *a, const u8 *b, con
     size_t threads = n * 4;
     k_verify_g2_quad<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, a, b, c, d, ok);
 }
-void run_final_exp_quad(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok) {
+void run_final_exp_quad(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok, void *fe_out) {
     if (!n) return;
-    k_final_exp_quad<<<(unsigned)((n * 4 + 127) / 128), 128, 0, st>>>(n, (const Fp *)fbuf, enc_ok, ok);
+    k_final_exp_quad<<<(unsigned)((n * 4 + 127) / 128), 128, 0, st>>>(n, (const Fp *)fbuf, enc_ok, ok, (Fp *)fe_out);
+}
+void run_final_exp_sm(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok, void *fe_out) {
+    if (!n) return;
+    k_final_exp_sm<<<(unsigned)((n * 4 + QNT - 1) / QNT), QNT, Q_SMEM_BYTES, st>>>(n, (const Fp *)fbuf, enc_ok, ok, (Fp *)fe_out);
 }
 void run_miller_quad_reg(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, void *fbuf, u8 *enc_ok) {
     if (!n) return;

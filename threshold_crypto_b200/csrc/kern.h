@@ -17,7 +17,8 @@ typedef uint64_t u64;
 cudaError_t upload_consts_pairing(const tcb::Consts &c);
 void run_verify_g2_quad(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok);
 void run_selftest(cudaStream_t st, size_t n, u64 seed, unsigned long long *bad);
-void run_final_exp_quad(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok);
+void run_final_exp_quad(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok, void *fe_out);   // register engine
+void run_final_exp_sm(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok, void *fe_out);     // products / squarings on cells
 void run_miller_quad_reg(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, void *fbuf, u8 *enc_ok);
 void run_count_diff(cudaStream_t st, size_t bytes, const void *x, const void *y, unsigned long long *bad);
 // ---- k_miller.cu  (shared-memory engine: operands staged in shared memory, dot-product form)

@@ -265,6 +265,77 @@ static __device__ __noinline__ void q_add_step(Fp qx, Fp qy, bool act) {
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Final exponentiation on cells: the two hot pieces (Fp12 products, Karabina compressed squarings) of quad.cuh's chain with their
+// operands in shared memory.  Slot map of that kernel: four Fp12 values V0..V3 (three slots each: my pair's coefficient halves),
+// six scratch slots.
+enum { QF_V0 = 0, QF_V1 = 3, QF_V2 = 6, QF_V3 = 9, QF_S0 = 12, QF_S1, QF_S2, QF_S3, QF_S4, QF_S5, QF_NSLOT };
+constexpr u32 QF_CA = QF_S4, QF_CB = QF_S5;         // the compressed value of the squaring chain: pair 0 (z4, z3), pair 1 (z2, z5)
+static_assert(QF_NSLOT == Q_NSLOT, "both kernels use the same shared-memory size");
+// r = x + y on the imaginary lane, x - y on the real lane (xi * (a + b u) = (a - b) + (a + b) u and friends)
+TCB_D Fp q_addsub(bool e, const Fp &x, const Fp &y) { return x + fp_select(e, y, -y); }
+// V[dst] <- V[a] * V[b]  (dst may be a or b).  pair 0: a0 b0 + v a1 b1;  pair 1: a0 b1 + a1 b0 — two Fp6 products per pair,
+// each three 6-term dots with the b-half resident (q_mul3x3), the xi-multiples of a's coefficients in scratch.
+static __device__ __noinline__ void qf_mul12(u32 dst, u32 a, u32 b) {
+    const u32 t = q_tid();
+    const bool e = q_role(), p0 = q_pair() == 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        Fp own = q_ld(a + 1 + k, t), part = q_ld(a + 1 + k, t ^ 1u);
+        q_st(QF_S0 + k, q_addsub(e, own, part));            // xi a_{1+k}
+    }
+    __syncwarp();
+    const u32 me = q_col_re(q_pair()), ot = q_col_re(q_pair() ^ 1u);
+    u32 ya = p0 ? me : ot;                                  // P: pair 0 a0 * b0 (own, own);  pair 1 a0 * b1 (a other, b own)
+    q_mul3x3(q_cell(b, me), q_cell(b + 1, me), q_cell(b + 2, me),
+             q_cell(a, ya), q_cell(QF_S1, ya), q_cell(QF_S0, ya),
+             q_cell(a + 1, ya), q_cell(a, ya), q_cell(QF_S1, ya),
+             q_cell(a + 2, ya), q_cell(a + 1, ya), q_cell(a, ya), QF_S2, QF_S3, QF_S4);
+    u32 yq = p0 ? ot : me;                                  // Q: pair 0 a1 * b1 (other, other);  pair 1 a1 * b0 (a own, b other)
+    q_mul3x3(q_cell(b, ot), q_cell(b + 1, ot), q_cell(b + 2, ot),
+             q_cell(a, yq), q_cell(QF_S1, yq), q_cell(QF_S0, yq),
+             q_cell(a + 1, yq), q_cell(a, yq), q_cell(QF_S1, yq),
+             q_cell(a + 2, yq), q_cell(a + 1, yq), q_cell(a, yq), dst, dst + 1, dst + 2);
+    Fp P0 = q_ld(QF_S2, t), P1 = q_ld(QF_S3, t), P2 = q_ld(QF_S4, t);
+    Fp Q0 = q_ld(dst, t), Q1 = q_ld(dst + 1, t), Q2 = q_ld(dst + 2, t), Q2p = q_ld(dst + 2, t ^ 1u);
+    Fp r0, r1, r2;
+    if (p0) { r0 = P0 + q_addsub(e, Q2, Q2p); r1 = P1 + Q0; r2 = P2 + Q1; }       // P + v Q,  v Q = (xi Q2, Q0, Q1)
+    else { r0 = P0 + Q0; r1 = P1 + Q1; r2 = P2 + Q2; }
+    __syncwarp();
+    q_st(dst, r0); q_st(dst + 1, r1); q_st(dst + 2, r2);
+    __syncwarp();
+}
+// One Karabina compressed squaring of (CA, CB) in place; same values as quad.cuh comp_sqr.
+static __device__ __noinline__ void qf_comp_sqr() {
+    const u32 t = q_tid(), o = t ^ 2u;
+    const bool e = q_role(), p0 = q_pair() == 0;
+    Fp a = q_ld(QF_CA, t);
+    q_st(QF_S0, a + q_ld(QF_CB, o));                        // pair 0: z4 + z5 ; pair 1: z2 + z3
+    __syncwarp();
+    Fp sA = q_sqr(QF_CA), sB = q_sqr(QF_CB), sC = q_sqr(QF_S0);
+    q_st(QF_S1, sA); q_st(QF_S2, sB); q_st(QF_S3, sC);
+    __syncwarp();
+    Fp xsB = q_addsub(e, sB, q_ld(QF_S2, t ^ 1u));          // xi * sB (mine)
+    Fp own = fp_select(p0, xsB, sB);                        // pair 0: xi z3^2 ; pair 1: z5^2
+    Fp osB = q_ld(QF_S2, o);
+    Fp rcv = fp_select(p0, q_addsub(e, osB, q_ld(QF_S2, o ^ 1u)), osB);     // pair 0: xi z5^2 ; pair 1: z3^2
+    Fp W = q_ld(QF_S1, o) + own;                            // pair 0: z2^2 + xi z3^2 ; pair 1: z4^2 + z5^2
+    Fp Q = sA + rcv;                                        // pair 0: z4^2 + xi z5^2 ; pair 1: z2^2 + z3^2
+    Fp d = q_ld(QF_S3, o) - W;
+    q_st(QF_S0, d);                                         // S0 was last read before the previous hand-off
+    __syncwarp();
+    Fp Ta = q_addsub(e, d, q_ld(QF_S0, t ^ 1u));            // pair 1: xi * 2 z4 z5
+    Fp Tb = sC - Q;                                         // pair 1: 2 z2 z3
+    Fp Pa = fp_select(p0, W, Ta), Pb = fp_select(p0, Q, Tb);
+    Fp b = q_ld(QF_CB, t);
+    Fp da = Pa + fp_select(p0, -a, a);                      // z4' = 3 Pa - 2 z4 | z2' = 3 Pa + 2 z2
+    Fp db = Pb + fp_select(p0, -b, b);                      // z3' = 3 Pb - 2 z3 | z5' = 3 Pb + 2 z5
+    Fp na = dbl(da) + Pa, nb = dbl(db) + Pb;
+    __syncwarp();
+    q_st(QF_CA, na); q_st(QF_CB, nb);
+    __syncwarp();
+}
+
 // ---- input staging: the block's slice of the four input arrays comes in as bulk asynchronous copies (TMA unit, 1-D) into the
 // (still unused) first slots, completion on an mbarrier; the lanes then decode their coordinates from shared memory with 128-bit
 // loads.  Unaligned caller pointers take a plain cooperative copy instead.

@@ -113,7 +113,8 @@ static int impl_verify_g2(tcb_ctx *ctx, DevState &dv, cudaStream_t st, size_t n,
     u8 *enc = (u8 *)arena_alloc(ctx, dv, n);
     if (!fbuf || !enc) return -1;
     RUN(run_miller_quad(st, n, a, b, c, d, fbuf, enc));
-    RUN(run_final_exp_quad(st, n, fbuf, enc, ok));
+    if (ctx->engine == TCB_ENGINE_QUAD_SMEM_FE) RUN(run_final_exp_sm(st, n, fbuf, enc, ok, nullptr));
+    else RUN(run_final_exp_quad(st, n, fbuf, enc, ok, nullptr));
     return 0;
 }
 static int impl_hash_g2(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
@@ -318,7 +319,7 @@ extern "C" void tcb_free(tcb_ctx *ctx) {
 }
 extern "C" const char *tcb_last_error(const tcb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" int tcb_set_engine(tcb_ctx *ctx, int engine) {
-    if (!ctx || (engine != TCB_ENGINE_QUAD_SMEM && engine != TCB_ENGINE_QUAD_REG)) return -2;
+    if (!ctx || (engine != TCB_ENGINE_QUAD_SMEM && engine != TCB_ENGINE_QUAD_REG && engine != TCB_ENGINE_QUAD_SMEM_FE)) return -2;
     ctx->engine = engine;
     return 0;
 }
@@ -373,7 +374,10 @@ extern "C" int tcb_miller_loop_batch_dev(tcb_ctx *ctx, void *stream, size_t n, c
 }
 extern "C" int tcb_final_exp_is_one_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const void *f_in, const u8 *enc_ok, u8 *ok) {
     DEV_PROLOGUE
-    if (n) RUN(run_final_exp_quad(st, n, f_in, enc_ok, ok));
+    if (n) {
+        if (ctx->engine == TCB_ENGINE_QUAD_SMEM_FE) RUN(run_final_exp_sm(st, n, f_in, enc_ok, ok, nullptr));
+        else RUN(run_final_exp_quad(st, n, f_in, enc_ok, ok, nullptr));
+    }
     DEV_RETURN(0);
 }
 extern "C" size_t tcb_miller_value_bytes(void) { return miller_f_bytes(); }
@@ -807,6 +811,16 @@ extern "C" int tcb_selftest_miller(tcb_ctx *ctx, size_t n, const u8 *a, const u8
     RUN(run_miller_quad_reg(st, n, da, db, dc, ddv, f2, e2));
     RUN(run_count_diff(st, fb, f1, f2, bad));
     RUN(run_count_diff(st, eb, e1, e2, bad));
+    // the two final-exponentiation kernels on the same Miller values: the full Fp12 results and the booleans must agree as well
+    void *g1 = arena_alloc(ctx, d, fb), *g2 = arena_alloc(ctx, d, fb);
+    u8 *o1 = (u8 *)arena_alloc(ctx, d, eb), *o2 = (u8 *)arena_alloc(ctx, d, eb);
+    if (!g1 || !g2 || !o1 || !o2) return -1;
+    CK(cudaMemsetAsync(o1, 0, eb, st));
+    CK(cudaMemsetAsync(o2, 0, eb, st));
+    RUN(run_final_exp_sm(st, n, f1, e1, o1, g1));
+    RUN(run_final_exp_quad(st, n, f1, e1, o2, g2));
+    RUN(run_count_diff(st, fb, g1, g2, bad));
+    RUN(run_count_diff(st, eb, o1, o2, bad));
     CK(cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return (int)(h > 0x7fffffff ? 0x7fffffff : h);
