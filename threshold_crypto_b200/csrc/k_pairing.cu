@@ -19,6 +19,9 @@ __global__ void __launch_bounds__(128, TCB_QUAD_MINB) k_verify_g2_quad(size_t n,
     bool res = pairing_eq_quad(a + 96 * i, b + 192 * i, c ? c + 96 * i : nullptr, d + 192 * i, enc_ok);
     if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok) ? 1 : 0;
 }
+// (Measured and dropped, profiles/kbench_r2i_fecells.json: keeping this kernel's saved compressed powers and prefix products in
+// shared-memory cells instead of its local frame.  The 110 KB carve-out leaves ~28 KB of L1 for the remaining 4 KB frames per
+// thread: 37.8 instead of 32.2 ms, DRAM write-back unchanged at 4.1 GB.  The register engine lives off the L1.)
 // Final exponentiation + "== 1" of the Miller-loop values produced by k_miller_quad (k_miller.cu) or k_miller_quad_reg:
 // f of item i, lane l, coefficient k at fin[(4 i + l) * 3 + k]  (576 B per item through HBM/L2).
 #ifndef TCB_FE_MINB

@@ -275,8 +275,11 @@ __device__ __noinline__ Fp12Q fp12_exp_by_x(const Fp12Q &f, u64 x) {
     if (x & 1) acc = fp12_mul(acc, f);
     return fp12_conj(acc);
 }
-// same chain as final_exponentiation<F2> in tower.cuh
-__device__ __noinline__ Fp12Q final_exponentiation(const Fp12Q &in) {
+// same chain as final_exponentiation<F2> in tower.cuh; X::exp(f, x) = conj(f^|x|) (the x-power runs are where the storage policy
+// differs: local arrays here, shared-memory cells in k_final_exp_quad)
+struct ExpLocal { TCB_D static Fp12Q exp(const Fp12Q &f, u64 x) { return fp12_exp_by_x(f, x); } };
+template <class X>
+__device__ __noinline__ Fp12Q final_exponentiation_with(const Fp12Q &in) {
     Fp12Q f2 = fp12_inv(in);
     TCB_PHASE();
     Fp12Q r = fp12_mul(fp12_conj(in), f2);
@@ -285,27 +288,28 @@ __device__ __noinline__ Fp12Q final_exponentiation(const Fp12Q &in) {
     TCB_PHASE();
     const u64 x = TCB_BLS_X;
     Fp12Q y0 = fp12_cyclo_sqr(r);
-    Fp12Q y1 = fp12_exp_by_x(y0, x);
-    Fp12Q y2 = fp12_exp_by_x(y1, x >> 1);
+    Fp12Q y1 = X::exp(y0, x);
+    Fp12Q y2 = X::exp(y1, x >> 1);
     Fp12Q y3 = fp12_conj(r);
     y1 = fp12_mul(y1, y3);
     y1 = fp12_conj(y1);
     y1 = fp12_mul(y1, y2);
-    y2 = fp12_exp_by_x(y1, x);
-    y3 = fp12_exp_by_x(y2, x);
+    y2 = X::exp(y1, x);
+    y3 = X::exp(y2, x);
     y1 = fp12_conj(y1);
     y3 = fp12_mul(y3, y1);
     y1 = fp12_conj(y1);
     y1 = fp12_frob(y1, 3);
     y2 = fp12_frob(y2, 2);
     y1 = fp12_mul(y1, y2);
-    y2 = fp12_exp_by_x(y3, x);
+    y2 = X::exp(y3, x);
     y2 = fp12_mul(y2, y0);
     y2 = fp12_mul(y2, r);
     y1 = fp12_mul(y1, y2);
     y2 = fp12_frob(y3, 1);
     return fp12_mul(y1, y2);
 }
+TCB_D Fp12Q final_exponentiation(const Fp12Q &in) { return final_exponentiation_with<ExpLocal>(in); }
 
 // ----------------------------------------------------------------------------- two-pairing Miller loop on a quad
 // Pair j holds (P_j, Q_j) and the running point T_j.  Per step each pair evaluates its own
