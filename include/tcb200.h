@@ -42,7 +42,8 @@ typedef struct tcb_ctx tcb_ctx;
 #define TCB_ENGINE_QUAD_SMEM 2 /* default: Miller loop with its operands staged in shared memory (dot-product form, TMA bulk input
                                   staging), f through HBM, then the final-exponentiation kernel (register engine) */
 #define TCB_ENGINE_QUAD_SMEM_FE 3 /* as 2, with the final exponentiation's Fp12 products and compressed squarings on shared-memory
-                                  cells as well (k_final_exp_sm): bit-identical, measured 32.7 vs 32.2 ms per 2^16 — kept for measurement */
+                                  cells as well (k_final_exp_sm, 12 slots): bit-identical, measured 32.5 vs 32.2 ms per 2^16 at 2 blocks/SM and 46 ms
+                                  at 3 blocks/SM (168 registers) — kept for measurement */
 
 int tcb_init(tcb_ctx **ctx, const int *device_ids, int n_devices);
 void tcb_free(tcb_ctx *ctx);

@@ -51,15 +51,14 @@ TCB_D Fp12Q qf_ld12(u32 v) {
 TCB_D void qf_st12(u32 v, const Fp12Q &a) {      // the caller hands off with __syncwarp()
     q_st(v, a.h.c0.h); q_st(v + 1, a.h.c1.h); q_st(v + 2, a.h.c2.h);
 }
-// V[dst] <- conj(V[src]^x): compressed chain on cells, decompression + product of the saved powers on the register engine
-static __device__ __noinline__ void qf_exp_by_x(u32 dst, u32 src, u64 x) {
+// V[v] <- conj(V[v]^x) in place: compressed chain on cells, decompression + product of the saved powers on the register engine
+static __device__ __noinline__ void qf_exp_by_x(u32 v, u64 x) {
     const u32 t = q_tid();
     const bool p0 = q_pair() == 0;
     int top = 63;
     while (!((x >> top) & 1)) top--;
     {
-        Fp a = q_ld(src + (p0 ? 1u : 0u), t), b = q_ld(src + 2, t);
-        __syncwarp();
+        Fp a = q_ld(v + (p0 ? 1u : 0u), t), b = q_ld(v + 2, t);
         q_st(QF_CA, a); q_st(QF_CB, b);
         __syncwarp();
     }
@@ -74,71 +73,64 @@ static __device__ __noinline__ void qf_exp_by_x(u32 dst, u32 src, u64 x) {
         }
     }
     Fp12Q acc;
-    if (want != ns || ns == 0 || !comp_decompress_product(saved, ns, acc)) acc = fp12_conj(fp12_exp_by_x_plain(qf_ld12(src), x));   // conj twice = id below
-    else if (x & 1) acc = fp12_mul(acc, qf_ld12(src));
+    if (want != ns || ns == 0 || !comp_decompress_product(saved, ns, acc)) acc = fp12_conj(fp12_exp_by_x_plain(qf_ld12(v), x));   // conj twice = id below
+    else if (x & 1) acc = fp12_mul(acc, qf_ld12(v));
     acc = fp12_conj(acc);
     __syncwarp();
-    qf_st12(dst, acc);
+    qf_st12(v, acc);
     __syncwarp();
 }
 TCB_D void qf_conj_inplace(u32 v) {              // own cells only
     if (q_pair()) { u32 t = q_tid(); for (u32 k = 0; k < 3; k++) q_st(v + k, -q_ld(v + k, t)); }
     __syncwarp();
 }
-// same chain as quad.cuh final_exponentiation; returns the result in registers
+TCB_D void qf_put(u32 v, const Fp12Q &a) { __syncwarp(); qf_st12(v, a); __syncwarp(); }
+// same chain as quad.cuh final_exponentiation; the running value is V0, the second operand of every product goes through V1
 static __device__ __noinline__ Fp12Q qf_final_exponentiation(const Fp12Q &in) {
     const u64 x = TCB_BLS_X;
     // easy part: r = (conj(in) * in^-1)^(p^2 + 1)
-    qf_st12(QF_V0, fp12_conj(in));
-    qf_st12(QF_V1, fp12_inv(in));
-    __syncwarp();
+    qf_put(QF_V0, fp12_conj(in));
+    qf_put(QF_V1, fp12_inv(in));
     qf_mul12(QF_V0, QF_V0, QF_V1);
     Fp12Q f2 = qf_ld12(QF_V0);
-    __syncwarp();
-    qf_st12(QF_V1, f2);
-    qf_st12(QF_V0, fp12_frob(f2, 2));
-    __syncwarp();
-    qf_mul12(QF_V0, QF_V0, QF_V1);                 // V0 = r
+    qf_put(QF_V1, f2);
+    qf_put(QF_V0, fp12_frob(f2, 2));
+    qf_mul12(QF_V0, QF_V0, QF_V1);
     Fp12Q r = qf_ld12(QF_V0);
     Fp12Q y0 = fp12_cyclo_sqr(r);
-    __syncwarp();
-    qf_st12(QF_V1, y0);
-    __syncwarp();
-    qf_exp_by_x(QF_V2, QF_V1, x);                  // y1
-    qf_exp_by_x(QF_V3, QF_V2, x >> 1);             // y2
-    qf_st12(QF_V1, fp12_conj(r));                  // y3 = conj(r)   (y0 and r are kept in registers / the local frame)
-    __syncwarp();
-    qf_mul12(QF_V2, QF_V2, QF_V1);                 // y1 = y1 * y3
-    qf_conj_inplace(QF_V2);
-    qf_mul12(QF_V2, QF_V2, QF_V3);                 // y1 = conj(y1) * y2
-    qf_exp_by_x(QF_V3, QF_V2, x);                  // y2 = y1^x
-    qf_exp_by_x(QF_V1, QF_V3, x);                  // y3 = y2^x
-    qf_conj_inplace(QF_V2);                        // y1 = conj(y1)
-    qf_mul12(QF_V1, QF_V1, QF_V2);                 // y3 = y3 * y1
-    qf_conj_inplace(QF_V2);                        // y1 = conj(y1)
-    {
-        Fp12Q y1 = fp12_frob(qf_ld12(QF_V2), 3), y2 = fp12_frob(qf_ld12(QF_V3), 2);
-        __syncwarp();
-        qf_st12(QF_V2, y1); qf_st12(QF_V3, y2);
-        __syncwarp();
-    }
-    qf_mul12(QF_V2, QF_V2, QF_V3);                 // y1 = y1 * y2
-    qf_exp_by_x(QF_V3, QF_V1, x);                  // y2 = y3^x
-    qf_st12(QF_V0, y0);
-    __syncwarp();
-    qf_mul12(QF_V3, QF_V3, QF_V0);                 // y2 = y2 * y0
-    qf_st12(QF_V0, r);
-    __syncwarp();
-    qf_mul12(QF_V3, QF_V3, QF_V0);                 // y2 = y2 * r
-    qf_mul12(QF_V2, QF_V2, QF_V3);                 // y1 = y1 * y2
-    {
-        Fp12Q y2 = fp12_frob(qf_ld12(QF_V1), 1);   // y2 = frob(y3)
-        __syncwarp();
-        qf_st12(QF_V3, y2);
-        __syncwarp();
-    }
-    qf_mul12(QF_V2, QF_V2, QF_V3);
-    return qf_ld12(QF_V2);
+    qf_put(QF_V0, y0);
+    qf_exp_by_x(QF_V0, x);
+    Fp12Q y1 = qf_ld12(QF_V0);                     // y1 = y0^x
+    qf_exp_by_x(QF_V0, x >> 1);
+    Fp12Q y2 = qf_ld12(QF_V0);                     // y2 = y1^(x/2)
+    qf_put(QF_V0, y1);
+    qf_put(QF_V1, fp12_conj(r));
+    qf_mul12(QF_V0, QF_V0, QF_V1);                 // y1 * conj(r)
+    qf_conj_inplace(QF_V0);
+    qf_put(QF_V1, y2);
+    qf_mul12(QF_V0, QF_V0, QF_V1);                 // y1 = conj(y1 conj(r)) * y2
+    y1 = qf_ld12(QF_V0);
+    qf_exp_by_x(QF_V0, x);
+    y2 = qf_ld12(QF_V0);                           // y2 = y1^x
+    qf_exp_by_x(QF_V0, x);                         // y3 = y2^x
+    qf_put(QF_V1, fp12_conj(y1));
+    qf_mul12(QF_V0, QF_V0, QF_V1);                 // y3 = y3 * conj(y1)
+    Fp12Q y3 = qf_ld12(QF_V0);
+    qf_put(QF_V0, fp12_frob(y1, 3));
+    qf_put(QF_V1, fp12_frob(y2, 2));
+    qf_mul12(QF_V0, QF_V0, QF_V1);
+    y1 = qf_ld12(QF_V0);                           // y1 = frob3(y1) * frob2(y2)
+    qf_put(QF_V0, y3);
+    qf_exp_by_x(QF_V0, x);                         // y3^x
+    qf_put(QF_V1, y0);
+    qf_mul12(QF_V0, QF_V0, QF_V1);
+    qf_put(QF_V1, r);
+    qf_mul12(QF_V0, QF_V0, QF_V1);                 // y2 = y3^x * y0 * r
+    qf_put(QF_V1, y1);
+    qf_mul12(QF_V0, QF_V0, QF_V1);                 // y1 * y2
+    qf_put(QF_V1, fp12_frob(y3, 1));
+    qf_mul12(QF_V0, QF_V0, QF_V1);
+    return qf_ld12(QF_V0);
 }
 #ifndef TCB_FESM_MINB
 #define TCB_FESM_MINB 2
@@ -331,7 +323,7 @@ cudaError_t upload_consts_pairing(const Consts &c) {
     // the pairing kernel keeps its small call frames in L1: no shared-memory carve-out
     cudaFuncSetAttribute(k_verify_g2_quad, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_final_exp_quad, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    if (cudaFuncSetAttribute(k_final_exp_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES) != cudaSuccess) return cudaErrorInvalidValue;
+    if (cudaFuncSetAttribute(k_final_exp_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QF_SMEM_BYTES) != cudaSuccess) return cudaErrorInvalidValue;
     cudaFuncSetAttribute(k_miller_quad_reg, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     return cudaMemcpyToSymbol(d_consts, &c, sizeof c);
 }
@@ -346,7 +338,7 @@ void run_final_exp_quad(cudaStream_t st, size_t n, const void *fbuf, const u8 *e
 }
 void run_final_exp_sm(cudaStream_t st, size_t n, const void *fbuf, const u8 *enc_ok, u8 *ok, void *fe_out) {
     if (!n) return;
-    k_final_exp_sm<<<(unsigned)((n * 4 + QNT - 1) / QNT), QNT, Q_SMEM_BYTES, st>>>(n, (const Fp *)fbuf, enc_ok, ok, (Fp *)fe_out);
+    k_final_exp_sm<<<(unsigned)((n * 4 + QNT - 1) / QNT), QNT, QF_SMEM_BYTES, st>>>(n, (const Fp *)fbuf, enc_ok, ok, (Fp *)fe_out);
 }
 void run_miller_quad_reg(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, void *fbuf, u8 *enc_ok) {
     if (!n) return;

@@ -267,11 +267,12 @@ static __device__ __noinline__ void q_add_step(Fp qx, Fp qy, bool act) {
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // Final exponentiation on cells: the two hot pieces (Fp12 products, Karabina compressed squarings) of quad.cuh's chain with their
-// operands in shared memory.  Slot map of that kernel: four Fp12 values V0..V3 (three slots each: my pair's coefficient halves),
-// six scratch slots.
-enum { QF_V0 = 0, QF_V1 = 3, QF_V2 = 6, QF_V3 = 9, QF_S0 = 12, QF_S1, QF_S2, QF_S3, QF_S4, QF_S5, QF_NSLOT };
+// operands in shared memory.  Slot map of that kernel: two Fp12 values V0, V1 (three slots each: my pair's coefficient halves)
+// and six scratch slots = 12 slots = 72 KB per 128-thread block (three blocks per SM); the other live values of the chain wait in
+// the thread's registers / local frame.
+enum { QF_V0 = 0, QF_V1 = 3, QF_S0 = 6, QF_S1, QF_S2, QF_S3, QF_S4, QF_S5, QF_NSLOT };
 constexpr u32 QF_CA = QF_S4, QF_CB = QF_S5;         // the compressed value of the squaring chain: pair 0 (z4, z3), pair 1 (z2, z5)
-static_assert(QF_NSLOT == Q_NSLOT, "both kernels use the same shared-memory size");
+constexpr size_t QF_SMEM_BYTES = (size_t)QF_NSLOT * 3 * QNT * 16;
 // r = x + y on the imaginary lane, x - y on the real lane (xi * (a + b u) = (a - b) + (a + b) u and friends)
 TCB_D Fp q_addsub(bool e, const Fp &x, const Fp &y) { return x + fp_select(e, y, -y); }
 // V[dst] <- V[a] * V[b]  (dst may be a or b).  pair 0: a0 b0 + v a1 b1;  pair 1: a0 b1 + a1 b0 — two Fp6 products per pair,
