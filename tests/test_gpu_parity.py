@@ -232,7 +232,7 @@ def test_both_pairing_engines_vs_oracle(gpu_engine, O):
     """tcb_set_engine: the round-1 register kernel and the shared-memory engine return the oracle's booleans, also for
     encodings >= p (ok = 0) and through device pointers that are NOT 16-byte aligned (plain-copy staging instead of TMA)."""
     import torch
-    from threshold_crypto_b200._lib import ENGINE_QUAD_REG, ENGINE_QUAD_SMEM, ENGINE_QUAD_SMEM_FE
+    from threshold_crypto_b200._lib import ENGINE_QUAD_REG, ENGINE_QUAD_SMEM, ENGINE_QUAD_SMEM_REGFE
     E = gpu_engine
     n = 45
     sk, pk, sig, msgs = cases.make_sig_batch(O, n, 92, corrupt_every=3)
@@ -242,7 +242,7 @@ def test_both_pairing_engines_vs_oracle(gpu_engine, O):
     exp = O.verify_g2_batch(pk, h, None, sig)
     assert exp[7] == 0 and 0 < exp.sum() < n
     try:
-        for eng in (ENGINE_QUAD_REG, ENGINE_QUAD_SMEM_FE, ENGINE_QUAD_SMEM):
+        for eng in (ENGINE_QUAD_REG, ENGINE_QUAD_SMEM_REGFE, ENGINE_QUAD_SMEM):
             E.set_engine(eng)
             assert np.array_equal(E.verify_g2_batch(pk, h, None, sig), exp)
             assert np.array_equal(E.verify_batch(pk, sig, msgs), exp)

@@ -16,8 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.environ.get("TCB200_LIB") or os.path.join(_HERE, "csrc", "libtcb200.so")
 
 ENGINE_QUAD_REG = 1      # round-1 fused register-engine pairing kernel (self-test reference, A/B measurement)
-ENGINE_QUAD_SMEM = 2     # default: shared-memory Miller loop + final-exponentiation kernel
-ENGINE_QUAD_SMEM_FE = 3  # as 2 with the final exponentiation's products / squarings on shared-memory cells too (measurement)
+ENGINE_QUAD_SMEM = 2     # default: Miller loop and final exponentiation on shared-memory cells (k_miller_quad + k_final_exp_sm)
+ENGINE_QUAD_SMEM_REGFE = 3  # shared-memory Miller loop + round 1's register-engine final exponentiation (A/B measurement)
 
 
 class TcbError(RuntimeError):

@@ -39,9 +39,10 @@ __global__ void __launch_bounds__(128, TCB_FE_MINB) k_final_exp_quad(size_t n, c
     if (live && fe_out) { Fp *o = fe_out + (i * 4 + (threadIdx.x & 3u)) * 3; stg_fp(o, g.h.c0.h); stg_fp(o + 1, g.h.c1.h); stg_fp(o + 2, g.h.c2.h); }
     if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok[i]) ? 1 : 0;
 }
-// ---- final exponentiation with its Fp12 products and compressed squarings on shared-memory cells (quadsm.cuh: qf_mul12,
-// qf_comp_sqr); the cold pieces (inversion, Frobenius maps, decompression of the saved powers, the first cyclotomic squaring)
-// stay on the register engine and move values through the cells' own columns.
+// ---- final exponentiation ENTIRELY on shared-memory cells (quadsm.cuh: qf_mul12, qf_comp_sqr + the pieces below): no Fp12 /
+// Fp6 value crosses a function boundary through the local frame.  Slots: V0 (running value), V1 (second operand), six scratch.
+// Same operations as quad.cuh's chain (same values, checked bit for bit by tcb_selftest_miller); the only local arrays are the
+// six saved compressed powers and the prefix products of an x-run (own halves: 864 B per thread).
 TCB_D Fp12Q qf_ld12(u32 v) {
     Fp12Q r;
     u32 t = q_tid();
@@ -51,57 +52,223 @@ TCB_D Fp12Q qf_ld12(u32 v) {
 TCB_D void qf_st12(u32 v, const Fp12Q &a) {      // the caller hands off with __syncwarp()
     q_st(v, a.h.c0.h); q_st(v + 1, a.h.c1.h); q_st(v + 2, a.h.c2.h);
 }
-// V[v] <- conj(V[v]^x) in place: compressed chain on cells, decompression + product of the saved powers on the register engine
-static __device__ __noinline__ void qf_exp_by_x(u32 v, u64 x) {
-    const u32 t = q_tid();
-    const bool p0 = q_pair() == 0;
-    int top = 63;
-    while (!((x >> top) & 1)) top--;
-    {
-        Fp a = q_ld(v + (p0 ? 1u : 0u), t), b = q_ld(v + 2, t);
-        q_st(QF_CA, a); q_st(QF_CB, b);
-        __syncwarp();
-    }
-    CompQ saved[COMP_MAX];
-    int ns = 0, want = 0;
-#pragma unroll 1
-    for (int i = 1; i <= top; i++) {
-        qf_comp_sqr();
-        if ((x >> i) & 1) {
-            want++;
-            if (ns < COMP_MAX) { saved[ns].a.h = q_ld(QF_CA, t); saved[ns].b.h = q_ld(QF_CB, t); ns++; }
-        }
-    }
-    Fp12Q acc;
-    if (want != ns || ns == 0 || !comp_decompress_product(saved, ns, acc)) acc = fp12_conj(fp12_exp_by_x_plain(qf_ld12(v), x));   // conj twice = id below
-    else if (x & 1) acc = fp12_mul(acc, qf_ld12(v));
-    acc = fp12_conj(acc);
+TCB_D void qf_copy12(u32 dst, u32 src) {         // own cells
+    u32 t = q_tid();
+    Fp a = q_ld(src, t), b = q_ld(src + 1, t), c = q_ld(src + 2, t);
     __syncwarp();
-    qf_st12(v, acc);
+    q_st(dst, a); q_st(dst + 1, b); q_st(dst + 2, c);
     __syncwarp();
 }
 TCB_D void qf_conj_inplace(u32 v) {              // own cells only
     if (q_pair()) { u32 t = q_tid(); for (u32 k = 0; k < 3; k++) q_st(v + k, -q_ld(v + k, t)); }
     __syncwarp();
 }
+static __device__ __noinline__ Fp q_fp_inv(Fp a) { return fp_inv(a); }
+// my half of the inverse of the Fp2 value whose my-half is `h` (exchange through cell `tmp`): conj(a) / norm(a)
+TCB_D Fp qf_inv2(const Fp &h, u32 tmp) {
+    Fp sq = h * h;
+    __syncwarp();
+    q_st(tmp, sq);
+    __syncwarp();
+    Fp n = q_fp_inv(sq + q_ld(tmp, q_tid() ^ 1u));
+    Fp r = h * n;
+    return q_role() ? -r : r;
+}
+// xi-multiples of the coefficients 1, 2 of V[a] (my pair) into S0, S1: what q_mul3x3 streams beside a Fp6 operand
+TCB_D void qf_xi12(u32 a) {
+    const u32 t = q_tid();
+    const bool e = q_role();
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        Fp own = q_ld(a + 1 + k, t), part = q_ld(a + 1 + k, t ^ 1u);
+        q_st(QF_S0 + k, q_addsub(e, own, part));
+    }
+    __syncwarp();
+}
+// dst (my column) <- A * B in Fp6, A = slots a.. at re-column ac (its xi-multiples in S0, S1 at the same column), B = slots b.. at bc
+TCB_D void qf_mul6(u32 dst, u32 a, u32 ac, u32 b, u32 bc) {
+    q_mul3x3(q_cell(b, bc), q_cell(b + 1, bc), q_cell(b + 2, bc),
+             q_cell(a, ac), q_cell(QF_S1, ac), q_cell(QF_S0, ac),
+             q_cell(a + 1, ac), q_cell(a, ac), q_cell(QF_S1, ac),
+             q_cell(a + 2, ac), q_cell(a + 1, ac), q_cell(a, ac), dst, dst + 1, dst + 2);
+}
+// V0 <- V0^-1 (uses V1 and the scratch): 1 / (c0 + c1 w) = (c0 - c1 w) / (c0^2 - v c1^2)
+static __device__ __noinline__ void qf_inv12() {
+    const u32 t = q_tid(), o = t ^ 2u, me = q_col_re(q_pair());
+    const bool e = q_role(), p0 = q_pair() == 0;
+    qf_xi12(QF_V0);
+    qf_mul6(QF_S2, QF_V0, me, QF_V0, me);                         // s = (my half)^2 in S2..S4
+    {
+        Fp s0 = q_ld(QF_S2, t), s1 = q_ld(QF_S3, t), s2 = q_ld(QF_S4, t);
+        Fp o0 = q_ld(QF_S2, o), o1 = q_ld(QF_S3, o), o2 = q_ld(QF_S4, o);
+        Fp X = fp_select(p0, o2, s2), Xp = q_ld(QF_S4, (p0 ? o : t) ^ 1u);
+        Fp xX = q_addsub(e, X, Xp);                                // xi * (other's s2 | my s2)
+        Fp t0 = fp_select(p0, s0, o0) - xX;                        // c0^2 - v c1^2 on both pairs
+        Fp t1 = fp_select(p0, s1 - o0, o1 - s0);
+        Fp t2 = fp_select(p0, s2 - o1, o2 - s1);
+        __syncwarp();
+        q_st(QF_V1, t0); q_st(QF_V1 + 1, t1); q_st(QF_V1 + 2, t2);
+        __syncwarp();
+    }
+    // Fp6 inverse of V1 (the same value on both pairs)
+    const u32 c0 = q_cell(QF_V1, me), c1 = q_cell(QF_V1 + 1, me), c2 = q_cell(QF_V1 + 2, me);
+    Fp sq0 = q_sqr(QF_V1), sq1 = q_sqr(QF_V1 + 1), sq2 = q_sqr(QF_V1 + 2);
+    Fp m12 = q_mul2(c1, c2), m01 = q_mul2(c0, c1), m02 = q_mul2(c0, c2);
+    q_st(QF_S0, m12); q_st(QF_S1, sq2);
+    __syncwarp();
+    Fp A0 = sq0 - q_addsub(e, m12, q_ld(QF_S0, t ^ 1u));
+    Fp A1 = q_addsub(e, sq2, q_ld(QF_S1, t ^ 1u)) - m01;
+    Fp A2 = sq1 - m02;
+    __syncwarp();
+    q_st(QF_S2, A0); q_st(QF_S3, A1); q_st(QF_S4, A2);
+    __syncwarp();
+    Fp u = q_mul2(c2, q_cell(QF_S3, me)) + q_mul2(c1, q_cell(QF_S4, me));
+    Fp w = q_mul2(c0, q_cell(QF_S2, me));
+    q_st(QF_S0, u);
+    __syncwarp();
+    Fp D = q_addsub(e, u, q_ld(QF_S0, t ^ 1u)) + w;
+    Fp dinv = qf_inv2(D, QF_S1);
+    __syncwarp();
+    q_st(QF_S0, dinv);
+    __syncwarp();
+    const u32 dc = q_cell(QF_S0, me);
+    Fp i0 = q_mul2(q_cell(QF_S2, me), dc), i1 = q_mul2(q_cell(QF_S3, me), dc), i2 = q_mul2(q_cell(QF_S4, me), dc);
+    __syncwarp();
+    q_st(QF_V1, i0); q_st(QF_V1 + 1, i1); q_st(QF_V1 + 2, i2);
+    __syncwarp();
+    qf_xi12(QF_V1);
+    qf_mul6(QF_V0, QF_V1, me, QF_V0, me);                         // my half * (c0^2 - v c1^2)^-1
+    qf_conj_inplace(QF_V0);
+}
+// V[v] <- V[v]^(p^k) in place: coefficient v^i w^j is conjugated k times and multiplied by frob[k][2 i + j]
+static __device__ __noinline__ void qf_frob(u32 v, int k) {
+    const Consts &C = CONSTS();
+    const u32 t = q_tid(), me = q_col_re(q_pair()), j = q_pair();
+    const bool e = q_role(), odd = k & 1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        Fp x = q_ld(v + i, t);
+        if (odd && e) x = -x;
+        const Fp2c &c = C.frob[k][2 * i + j];
+        q_st(v + i, x);
+        q_st(QF_S0 + i, e ? c.c1 : c.c0);
+    }
+    __syncwarp();
+    Fp r0 = q_mul2(q_cell(v, me), q_cell(QF_S0, me)), r1 = q_mul2(q_cell(v + 1, me), q_cell(QF_S1, me)), r2 = q_mul2(q_cell(v + 2, me), q_cell(QF_S2, me));
+    __syncwarp();
+    q_st(v, r0); q_st(v + 1, r1); q_st(v + 2, r2);
+    __syncwarp();
+}
+// V0 <- product of the decompressed saved powers; false (warp-uniform result is formed by the caller) if a z2 is zero.
+// z1 = (xi z5^2 + 3 z4^2 - 2 z3) / (4 z2),  z0 = (2 z1^2 + z2 z5 - 3 z3 z4) xi + 1; one shared inversion (Montgomery's trick).
+static __device__ __noinline__ bool qf_decompress_product(const Fp *sa, const Fp *sb, int n) {
+    const u32 t = q_tid(), o = t ^ 2u, me = q_col_re(q_pair());
+    const bool e = q_role(), p0 = q_pair() == 0;
+    Fp pre[COMP_MAX];
+    Fp one = e ? Fp::zero() : fp_one();
+    bool bad = false;
+    q_st(QF_S2, one);                                              // running product of the denominators
+    __syncwarp();
+    for (int k = 0; k < n; k++) {
+        Fp den = dbl(dbl(sa[k]));                                  // pair 1: 4 z2
+        bool z = pair_and(den.is_zero());
+        bad = bad || (!p0 && z);
+        pre[k] = q_ld(QF_S2, t);
+        q_st(QF_S3, den);
+        __syncwarp();
+        Fp run = q_mul2(q_cell(QF_S2, me), q_cell(QF_S3, me));
+        __syncwarp();
+        q_st(QF_S2, run);
+        __syncwarp();
+    }
+    if (!q_quad_and(!bad)) bad = true;                             // quad-uniform
+    if (__any_sync(0xffffffffu, bad)) return false;                // warp-uniform: the caller redoes the whole warp the plain way
+    Fp rinv = qf_inv2(q_ld(QF_S2, t), QF_S3);
+    for (int k = n - 1; k >= 0; k--) {
+        __syncwarp();
+        q_st(QF_S2, rinv); q_st(QF_S3, pre[k]); q_st(QF_S0, dbl(dbl(sa[k]))); q_st(QF_CA, sa[k]); q_st(QF_CB, sb[k]);
+        __syncwarp();
+        Fp dinv = q_mul2(q_cell(QF_S2, me), q_cell(QF_S3, me));
+        rinv = q_mul2(q_cell(QF_S2, me), q_cell(QF_S0, me));
+        Fp s = q_sqr(p0 ? QF_CA : QF_CB);                          // pair 0: z4^2 ; pair 1: z5^2
+        Fp m = q_mul2(q_cell(QF_CA, me), q_cell(QF_CB, me));       // pair 0: z4 z3 ; pair 1: z2 z5
+        __syncwarp();
+        q_st(QF_S3, dinv); q_st(QF_S1, s);
+        __syncwarp();
+        Fp os = q_ld(QF_S1, o);
+        Fp num = q_addsub(e, s, q_ld(QF_S1, t ^ 1u)) + (dbl(os) + os) - dbl(q_ld(QF_CB, o));     // pair 1: xi z5^2 + 3 z4^2 - 2 z3
+        q_st(QF_S0, num);
+        __syncwarp();
+        Fp z1 = q_mul2(q_cell(QF_S0, me), q_cell(QF_S3, me));
+        __syncwarp();
+        q_st(QF_S1, z1);
+        __syncwarp();
+        Fp w = dbl(q_sqr(QF_S1)) + m;                              // pair 1: 2 z1^2 + z2 z5
+        q_st(QF_S0, w);
+        __syncwarp();
+        Fp u = q_ld(QF_S0, o) - (dbl(m) + m);                      // pair 0: 2 z1^2 + z2 z5 - 3 z3 z4
+        q_st(QF_S3, u);
+        __syncwarp();
+        Fp z0 = q_addsub(e, u, q_ld(QF_S3, t ^ 1u)) + one;
+        const u32 dst = (k == n - 1) ? QF_V0 : QF_V1;
+        q_st(dst, fp_select(p0, z0, sa[k])); q_st(dst + 1, fp_select(p0, sa[k], z1)); q_st(dst + 2, sb[k]);     // (z0, z4, z3) | (z2, z1, z5)
+        __syncwarp();
+        if (k != n - 1) qf_mul12(QF_V0, QF_V0, QF_V1);
+    }
+    return true;
+}
+// V0 <- conj(V0^x) in place
+static __device__ __noinline__ void qf_exp_by_x(u64 x) {
+    const u32 t = q_tid();
+    const bool p0 = q_pair() == 0;
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+    Fp12Q f = qf_ld12(QF_V0);                                      // kept for the (rare) plain path
+    q_st(QF_CA, p0 ? f.h.c1.h : f.h.c0.h); q_st(QF_CB, f.h.c2.h);
+    __syncwarp();
+    Fp sa[COMP_MAX], sb[COMP_MAX];
+    int ns = 0;
+#pragma unroll 1
+    for (int i = 1; i <= top; i++) {
+        qf_comp_sqr();
+        if (((x >> i) & 1) && ns < COMP_MAX) { sa[ns] = q_ld(QF_CA, t); sb[ns] = q_ld(QF_CB, t); ns++; }
+    }
+    int want = 0;
+    for (int i = 1; i <= top; i++) want += (int)((x >> i) & 1);
+    bool ok = ns > 0 && want == ns && qf_decompress_product(sa, sb, ns);        // warp-uniform
+    if (ok) {
+        if (x & 1) { __syncwarp(); qf_st12(QF_V1, f); __syncwarp(); qf_mul12(QF_V0, QF_V0, QF_V1); }
+    } else {
+        // some quad of the warp holds a value with z2 = 0 (f = 1 when both pairings are skipped): plain square-and-multiply, whole warp
+        __syncwarp();
+        qf_st12(QF_V0, f); qf_st12(QF_V1, f);
+        __syncwarp();
+        for (int i = top - 1; i >= 0; i--) {
+            qf_mul12(QF_V0, QF_V0, QF_V0);
+            if ((x >> i) & 1) qf_mul12(QF_V0, QF_V0, QF_V1);
+        }
+    }
+    qf_conj_inplace(QF_V0);
+}
 TCB_D void qf_put(u32 v, const Fp12Q &a) { __syncwarp(); qf_st12(v, a); __syncwarp(); }
-// same chain as quad.cuh final_exponentiation; the running value is V0, the second operand of every product goes through V1
-static __device__ __noinline__ Fp12Q qf_final_exponentiation(const Fp12Q &in) {
+// same chain as quad.cuh final_exponentiation; the running value is V0, the second operand of every product goes through V1;
+// the other live values (r, y0..y3) wait in the local frame as own halves
+static __device__ __noinline__ bool qf_final_exp_is_one(const Fp12Q &in, Fp12Q &out) {
     const u64 x = TCB_BLS_X;
     // easy part: r = (conj(in) * in^-1)^(p^2 + 1)
-    qf_put(QF_V0, fp12_conj(in));
-    qf_put(QF_V1, fp12_inv(in));
+    qf_put(QF_V0, in);
+    qf_inv12();
+    qf_put(QF_V1, fp12_conj(in));
     qf_mul12(QF_V0, QF_V0, QF_V1);
-    Fp12Q f2 = qf_ld12(QF_V0);
-    qf_put(QF_V1, f2);
-    qf_put(QF_V0, fp12_frob(f2, 2));
+    qf_copy12(QF_V1, QF_V0);
+    qf_frob(QF_V0, 2);
     qf_mul12(QF_V0, QF_V0, QF_V1);
     Fp12Q r = qf_ld12(QF_V0);
-    Fp12Q y0 = fp12_cyclo_sqr(r);
-    qf_put(QF_V0, y0);
-    qf_exp_by_x(QF_V0, x);
+    qf_mul12(QF_V0, QF_V0, QF_V0);                 // y0 = r^2 (r is in the cyclotomic subgroup: the plain square is the cyclotomic one)
+    Fp12Q y0 = qf_ld12(QF_V0);
+    qf_exp_by_x(x);
     Fp12Q y1 = qf_ld12(QF_V0);                     // y1 = y0^x
-    qf_exp_by_x(QF_V0, x >> 1);
+    qf_exp_by_x(x >> 1);
     Fp12Q y2 = qf_ld12(QF_V0);                     // y2 = y1^(x/2)
     qf_put(QF_V0, y1);
     qf_put(QF_V1, fp12_conj(r));
@@ -110,27 +277,36 @@ static __device__ __noinline__ Fp12Q qf_final_exponentiation(const Fp12Q &in) {
     qf_put(QF_V1, y2);
     qf_mul12(QF_V0, QF_V0, QF_V1);                 // y1 = conj(y1 conj(r)) * y2
     y1 = qf_ld12(QF_V0);
-    qf_exp_by_x(QF_V0, x);
+    qf_exp_by_x(x);
     y2 = qf_ld12(QF_V0);                           // y2 = y1^x
-    qf_exp_by_x(QF_V0, x);                         // y3 = y2^x
+    qf_exp_by_x(x);                                // y3 = y2^x
     qf_put(QF_V1, fp12_conj(y1));
     qf_mul12(QF_V0, QF_V0, QF_V1);                 // y3 = y3 * conj(y1)
     Fp12Q y3 = qf_ld12(QF_V0);
-    qf_put(QF_V0, fp12_frob(y1, 3));
-    qf_put(QF_V1, fp12_frob(y2, 2));
+    qf_put(QF_V0, y2);
+    qf_frob(QF_V0, 2);
+    qf_copy12(QF_V1, QF_V0);
+    qf_put(QF_V0, y1);
+    qf_frob(QF_V0, 3);
     qf_mul12(QF_V0, QF_V0, QF_V1);
     y1 = qf_ld12(QF_V0);                           // y1 = frob3(y1) * frob2(y2)
     qf_put(QF_V0, y3);
-    qf_exp_by_x(QF_V0, x);                         // y3^x
+    qf_exp_by_x(x);                                // y3^x
     qf_put(QF_V1, y0);
     qf_mul12(QF_V0, QF_V0, QF_V1);
     qf_put(QF_V1, r);
     qf_mul12(QF_V0, QF_V0, QF_V1);                 // y2 = y3^x * y0 * r
     qf_put(QF_V1, y1);
     qf_mul12(QF_V0, QF_V0, QF_V1);                 // y1 * y2
-    qf_put(QF_V1, fp12_frob(y3, 1));
+    y1 = qf_ld12(QF_V0);
+    qf_put(QF_V0, y3);
+    qf_frob(QF_V0, 1);
+    qf_put(QF_V1, y1);
     qf_mul12(QF_V0, QF_V0, QF_V1);
-    return qf_ld12(QF_V0);
+    out = qf_ld12(QF_V0);
+    bool p0 = q_pair() == 0, e = q_role();
+    Fp want = (p0 && !e) ? fp_one() : Fp::zero();
+    return q_quad_and(out.h.c0.h == want && out.h.c1.h.is_zero() && out.h.c2.h.is_zero());
 }
 #ifndef TCB_FESM_MINB
 #define TCB_FESM_MINB 2
@@ -143,8 +319,8 @@ __global__ void __launch_bounds__(QNT, TCB_FESM_MINB) k_final_exp_sm(size_t n, c
     const Fp *p = fin + (i * 4 + (threadIdx.x & 3u)) * 3;
     Fp12Q f;
     f.h.c0.h = ldg_fp(p); f.h.c1.h = ldg_fp(p + 1); f.h.c2.h = ldg_fp(p + 2);
-    Fp12Q g = qf_final_exponentiation(fp12_conj(f));
-    bool res = fp12_is_one(g);
+    Fp12Q g;
+    bool res = qf_final_exp_is_one(fp12_conj(f), g);
     if (live && fe_out) { Fp *o = fe_out + (i * 4 + (threadIdx.x & 3u)) * 3; stg_fp(o, g.h.c0.h); stg_fp(o + 1, g.h.c1.h); stg_fp(o + 2, g.h.c2.h); }
     if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok[i]) ? 1 : 0;
 }

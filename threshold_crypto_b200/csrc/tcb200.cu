@@ -4,8 +4,9 @@
 // every entry point enqueues CUDA kernels or fails with an error code.
 //
 // Kernel inventory:
-//   k_miller_quad + k_final_exp_quad   a1/a3  pairing equality, one item per lane QUAD: Miller loop with its operands staged in
-//                               shared memory (quadsm.cuh), f through HBM, final exponentiation on the register engine (quad.cuh)
+//   k_miller_quad + k_final_exp_sm   a1/a3  pairing equality, one item per lane QUAD: Miller loop and final exponentiation with their
+//                               operands staged in shared memory (quadsm.cuh), f through HBM between the two
+//   k_final_exp_quad            the round-1 register-engine final exponentiation (TCB_ENGINE_QUAD_SMEM_REGFE: A/B measurement, self-test reference)
 //   k_verify_g2_quad            the round-1 fused register-engine kernel (TCB_ENGINE_QUAD_REG: self-test reference, A/B measurement)
 //   k_hash_g2                   a2     SHA3 -> ChaCha20 -> G2::random -> exact cofactor (lane pairs)
 //   k_sign                      a4     sk * H(m)                                   (lane pairs)
@@ -113,8 +114,8 @@ static int impl_verify_g2(tcb_ctx *ctx, DevState &dv, cudaStream_t st, size_t n,
     u8 *enc = (u8 *)arena_alloc(ctx, dv, n);
     if (!fbuf || !enc) return -1;
     RUN(run_miller_quad(st, n, a, b, c, d, fbuf, enc));
-    if (ctx->engine == TCB_ENGINE_QUAD_SMEM_FE) RUN(run_final_exp_sm(st, n, fbuf, enc, ok, nullptr));
-    else RUN(run_final_exp_quad(st, n, fbuf, enc, ok, nullptr));
+    if (ctx->engine == TCB_ENGINE_QUAD_SMEM_REGFE) RUN(run_final_exp_quad(st, n, fbuf, enc, ok, nullptr));
+    else RUN(run_final_exp_sm(st, n, fbuf, enc, ok, nullptr));
     return 0;
 }
 static int impl_hash_g2(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
@@ -319,7 +320,7 @@ extern "C" void tcb_free(tcb_ctx *ctx) {
 }
 extern "C" const char *tcb_last_error(const tcb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" int tcb_set_engine(tcb_ctx *ctx, int engine) {
-    if (!ctx || (engine != TCB_ENGINE_QUAD_SMEM && engine != TCB_ENGINE_QUAD_REG && engine != TCB_ENGINE_QUAD_SMEM_FE)) return -2;
+    if (!ctx || (engine != TCB_ENGINE_QUAD_SMEM && engine != TCB_ENGINE_QUAD_REG && engine != TCB_ENGINE_QUAD_SMEM_REGFE)) return -2;
     ctx->engine = engine;
     return 0;
 }
@@ -375,7 +376,7 @@ extern "C" int tcb_miller_loop_batch_dev(tcb_ctx *ctx, void *stream, size_t n, c
 extern "C" int tcb_final_exp_is_one_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const void *f_in, const u8 *enc_ok, u8 *ok) {
     DEV_PROLOGUE
     if (n) {
-        if (ctx->engine == TCB_ENGINE_QUAD_SMEM_FE) RUN(run_final_exp_sm(st, n, f_in, enc_ok, ok, nullptr));
+        if (ctx->engine == TCB_ENGINE_QUAD_SMEM) RUN(run_final_exp_sm(st, n, f_in, enc_ok, ok, nullptr));
         else RUN(run_final_exp_quad(st, n, f_in, enc_ok, ok, nullptr));
     }
     DEV_RETURN(0);
