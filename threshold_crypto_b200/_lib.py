@@ -94,7 +94,8 @@ class Engine:
         self._ck(self.lib.tcb_set_msm_groups(self.ctx, C.c_size_t(int(groups))))
 
     def set_msm_algo(self, algo):
-        """0 Straus / shared doublings (default), 1 batch-affine tree, 2 one multiplication per share."""
+        """0 Straus / shared doublings (default), 1 batch-affine tree, 2 one multiplication per share, 3 G2 accumulation per thread,
+        4 G2 accumulation on shared-memory cells."""
         self._ck(self.lib.tcb_set_msm_algo(self.ctx, int(algo)))
 
     def set_eval_split(self, units):

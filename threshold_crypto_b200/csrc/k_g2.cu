@@ -6,6 +6,7 @@
 #define TCB_FP_POW_CALL 1      // fixed-exponent powers (square roots) call one shared Fp multiply (tower.cuh)
 #include "kern.h"
 #include "scheme.cuh"
+#include "g2sm.cuh"
 using namespace tcb;
 typedef Fp2S F2;
 #ifndef TCB_G2_MINB
@@ -43,6 +44,13 @@ __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_acc(size_t units, s
     size_t i = unit_index();
     if (i < units) task_g2_msm_acc<F2>(i, m, G, tab, dg, out);
 }
+// the same accumulation with the running point, the table entry and the temporaries in shared-memory cells (g2sm.cuh): 4 blocks/SM
+#ifndef TCB_G2SM_MINB
+#define TCB_G2SM_MINB 4
+#endif
+__global__ void __launch_bounds__(QNT, TCB_G2SM_MINB) k_g2_msm_acc_sm(size_t units, size_t m, size_t G, const AffStore<F2> *tab, const Gls4Digits *dg, JacStore<F2> *out) {
+    g2_msm_acc_cells(units, m, G, tab, dg, out);
+}
 __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_acc_ba(size_t units, size_t m, size_t G, const AffStore<F2> *tab, const Gls4Digits *dg,
                                                                    AffStore<F2> *buf_a, AffStore<F2> *buf_b, Fp2c *prefix, size_t cnt_max, JacStore<F2> *out) {
     size_t i = unit_index();
@@ -58,7 +66,11 @@ __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_decompress(size_t n, co
 }
 namespace tcbk {
 static inline unsigned grid2(size_t units) { return (unsigned)((units * 2 + 127) / 128); }
-cudaError_t upload_consts_g2(const Consts &c) { return cudaMemcpyToSymbol(d_consts, &c, sizeof c); }
+cudaError_t upload_consts_g2(const Consts &c) {
+    cudaError_t e = cudaFuncSetAttribute(k_g2_msm_acc_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES);    // per device
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(d_consts, &c, sizeof c);
+}
 void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     if (n) k_hash_g2<<<grid2(n), 128, 0, st>>>(n, msgs, off, out);
 }
@@ -86,6 +98,16 @@ void run_g2_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts,
 }
 void run_g2_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out) {
     if (units) k_g2_msm_acc<<<grid2(units), 128, 0, st>>>(units, m, G, (const AffStore<F2> *)tab, (const Gls4Digits *)dg, (JacStore<F2> *)out);
+}
+size_t g2_msm_sm_units_per_sm() {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_g2_msm_acc_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES); attr = true; }
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_g2_msm_acc_sm, QNT, G_SMEM_BYTES) != cudaSuccess || blocks < 1) blocks = 1;
+    return (size_t)blocks * (QNT / 2);
+}
+void run_g2_msm_acc_sm(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out) {
+    if (units) k_g2_msm_acc_sm<<<(unsigned)((units * 2 + QNT - 1) / QNT), QNT, G_SMEM_BYTES, st>>>(units, m, G, (const AffStore<F2> *)tab, (const Gls4Digits *)dg, (JacStore<F2> *)out);
 }
 size_t g2_msm_ba_units_per_sm() {
     int blocks = 0;

@@ -66,12 +66,12 @@ TCB_D void qf_conj_inplace(u32 v) {              // own cells only
 static __device__ __noinline__ Fp q_fp_inv(Fp a) { return fp_inv(a); }
 // my half of the inverse of the Fp2 value whose my-half is `h` (exchange through cell `tmp`): conj(a) / norm(a)
 TCB_D Fp qf_inv2(const Fp &h, u32 tmp) {
-    Fp sq = h * h;
+    Fp sq = q_fmul(h, h);
     __syncwarp();
     q_st(tmp, sq);
     __syncwarp();
     Fp n = q_fp_inv(sq + q_ld(tmp, q_tid() ^ 1u));
-    Fp r = h * n;
+    Fp r = q_fmul(h, n);
     return q_role() ? -r : r;
 }
 // xi-multiples of the coefficients 1, 2 of V[a] (my pair) into S0, S1: what q_mul3x3 streams beside a Fp6 operand

@@ -102,6 +102,21 @@ TCB_D Fp q_dot(const u32 (*x)[12], const u32 *vre) {
     }
     return dot_finish<FpParams, 2 * T>(even, odd);
 }
+// an Fp in global memory as three 128-bit vectors (scratch buffers are 16-byte aligned)
+TCB_D Fp ldg_fp2(const Fp *p) {
+    const uint4 *q = (const uint4 *)p;
+    uint4 a = q[0], b = q[1], c = q[2];
+    Fp r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
+    return r;
+}
+TCB_D void stg_fp2(Fp *p, const Fp &v) {
+    uint4 *q = (uint4 *)p;
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]); q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]); q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
+}
+// single Fp product as a call (by-value ABI: operands and result in registers) whatever the translation unit inlines elsewhere
+static __device__ __noinline__ Fp q_fmul(Fp a, Fp b) { return mmul<FpParams>(a, b); }
 // Fp2 product of two cell-resident values (my half)
 static __device__ __noinline__ Fp q_mul2(u32 ure, u32 vre) {
     u32 x[2][12];
@@ -114,7 +129,7 @@ TCB_D Fp q_sqr(u32 s) {
     bool e = q_role();
     Fp x = own + fp_select(e, own, part);
     Fp y = fp_select(e, part, own - part);
-    return x * y;
+    return q_fmul(x, y);
 }
 // Three 3-term Fp2 dot products with the SAME left operands (u0, u1, u2):  r_d = sum_t U_t * V_{d,t}.  The results are written
 // to the slots d0..d2 (my column) after every lane of the warp has finished reading, so they may alias the operands.
@@ -202,7 +217,7 @@ static __device__ __noinline__ void q_sqr12() {
 TCB_D void q_store_line(const Fp &lc, const Fp &lb, const Fp &la, bool act) {
     const u32 pc = q_col_re(q_pair());
     Fp px = q_ld(Q_P, pc), py = q_ld(Q_P, pc + 1);
-    Fp l1 = lb * px, l4 = la * py;
+    Fp l1 = q_fmul(lb, px), l4 = q_fmul(la, py);
     Fp one = q_role() ? Fp::zero() : fp_one();
     q_st(Q_L0, act ? lc : one);
     q_st(Q_L1, act ? l1 : Fp::zero());

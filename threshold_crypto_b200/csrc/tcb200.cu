@@ -149,7 +149,7 @@ static size_t pick_groups(size_t n, size_t m, size_t units_per_wave, double fixe
     }
     return best;
 }
-enum { MSM_STRAUS = 0, MSM_BATCH_AFFINE = 1, MSM_PER_SHARE = 2, MSM_STRAUS_G2_THREAD = 3 };
+enum { MSM_STRAUS = 0, MSM_BATCH_AFFINE = 1, MSM_PER_SHARE = 2, MSM_STRAUS_G2_THREAD = 3, MSM_STRAUS_G2_CELLS = 4 };
 // out: G Jacobian partial sums per item in `part` (then run_g*_sum(n, G, part, ...))
 static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
     const size_t term = g2 ? g2_term_bytes() : g1_term_bytes();
@@ -163,9 +163,12 @@ static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t 
     }
     const bool ba = ctx->msm_algo == MSM_BATCH_AFFINE;
     const bool g2_thread = g2 && ctx->msm_algo == MSM_STRAUS_G2_THREAD;
-    static size_t per_sm[5] = {0, 0, 0, 0, 0};
-    size_t &ps = per_sm[g2_thread ? 4 : (g2 ? 2 : 0) + (ba ? 1 : 0)];
-    if (!ps) ps = g2_thread ? g2_msm_thread_units_per_sm() : g2 ? (ba ? g2_msm_ba_units_per_sm() : g2_msm_units_per_sm()) : (ba ? g1_msm_ba_units_per_sm() : g1_msm_units_per_sm());
+    // the G2 accumulation on shared-memory cells (g2sm.cuh, 4 blocks/SM): measured 23.0 vs 19.3 ms at 2^14 items (G = 2 costs 17 % more
+    // multiply-accumulates and the multiply pipe is the limit either way), 4.2 vs 4.6 ms at 2048 items — a measurement knob, not the default
+    const bool g2_cells = g2 && ctx->msm_algo == MSM_STRAUS_G2_CELLS;
+    static size_t per_sm[6] = {0, 0, 0, 0, 0, 0};
+    size_t &ps = per_sm[g2_cells ? 5 : g2_thread ? 4 : (g2 ? 2 : 0) + (ba ? 1 : 0)];
+    if (!ps) ps = g2_cells ? g2_msm_sm_units_per_sm() : g2_thread ? g2_msm_thread_units_per_sm() : g2 ? (ba ? g2_msm_ba_units_per_sm() : g2_msm_units_per_sm()) : (ba ? g1_msm_ba_units_per_sm() : g1_msm_units_per_sm());
     // relative costs in field multiplications: doubling 4.8 / 7, mixed addition 8.6 / 11, affine addition ~5.7 (+ one inversion per tree level)
     // (G1 reads two digit positions per look-up: two doublings per position)
     double fixed = g2 ? (ba ? 4.8 + 8.6 + 6.0 : 4.8) : (ba ? 14.0 + 11.0 + 6.0 : 14.0);
@@ -179,6 +182,7 @@ static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t 
     else RUN(run_g1_msm_prep(st, n * m, k, pts, tab, dg, status, m));
     if (!ba) {
         if (g2_thread) RUN(run_g2_msm_acc_thread(st, n * G, m, G, tab, dg, part));
+        else if (g2_cells) RUN(run_g2_msm_acc_sm(st, n * G, m, G, tab, dg, part));
         else if (g2) RUN(run_g2_msm_acc(st, n * G, m, G, tab, dg, part));
         else RUN(run_g1_msm_acc(st, n * G, m, G, tab, dg, part));
         return 0;
@@ -273,7 +277,7 @@ extern "C" int tcb_init(tcb_ctx **out, const int *device_ids, int n_devices) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return -3;   // no CPU fallback
     tcb_ctx *ctx = new tcb_ctx();
-    { const char *e = getenv("TCB200_MSM_ALGO"); if (e && e[0] >= '0' && e[0] <= '3') ctx->msm_algo = e[0] - '0'; }
+    { const char *e = getenv("TCB200_MSM_ALGO"); if (e && e[0] >= '0' && e[0] <= '4') ctx->msm_algo = e[0] - '0'; }
     Consts C;
     build_consts(C);
     if (n_devices <= 0 || !device_ids) {
@@ -336,7 +340,7 @@ extern "C" int tcb_set_eval_split(tcb_ctx *ctx, size_t units) {
     return 0;
 }
 extern "C" int tcb_set_msm_algo(tcb_ctx *ctx, int algo) {
-    if (!ctx || algo < 0 || algo > 3) return -2;
+    if (!ctx || algo < 0 || algo > 4) return -2;
     ctx->msm_algo = algo;
     return 0;
 }
