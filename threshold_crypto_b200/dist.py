@@ -67,7 +67,7 @@ class ShardedEngine:
     def _is_root(self):
         return self.rank == self.root
 
-    def _to_dev(self, host, pin_ok=True):
+    def _to_dev(self, host):
         """root: host numpy array -> flat uint8 tensor on the compute device (async H2D on the current stream)"""
         if isinstance(host, torch.Tensor):
             t = host.contiguous().view(torch.uint8).reshape(-1)
