@@ -49,6 +49,16 @@ int tcb_init(tcb_ctx **ctx, const int *device_ids, int n_devices);
 void tcb_free(tcb_ctx *ctx);
 const char *tcb_last_error(const tcb_ctx *ctx);
 int tcb_set_engine(tcb_ctx *ctx, int engine);
+/* How tcb_verify_batch (PublicKey::verify, src/lib.rs:115-117) forms the message point.  0 (default): the hash kernel stops at
+ * Q0 = [3 (x^2 - 1)] H(m) (two of the three 64-bit multiplications of the exact cofactor clearing) and the check is
+ * e(pk, Q0) == e([3 (x^2 - 1)] g1, sig) with the constant multiple of the generator — 3 (x^2 - 1) is a unit mod r, so this is
+ * the same boolean as e(pk, H(m)) == e(g1, sig).  1: the exact H(m) of tcb_hash_g2_batch and the plain generator (A/B
+ * measurement, cross-check in the tests).  tcb_hash_g2_batch / tcb_sign_batch always produce the exact point. */
+int tcb_set_verify_hash(tcb_ctx *ctx, int exact);
+/* hash_g2 (tcb_hash_g2_batch and inside tcb_verify_batch): 0 (default) two kernels — SHA3 / ChaCha / candidate search / square
+ * root with one THREAD per item (k_hash_g2_point), cofactor clearing on lane pairs (k_g2_clear); 1 the one-kernel lane-pair
+ * version (k_hash_g2), in which the two Fp powers of the square root run redundantly on both lanes.  Same outputs. */
+int tcb_set_hash_algo(tcb_ctx *ctx, int algo);
 /* Tuning knob of the multi-scalar multiplication behind combine / decrypt / lincomb: partial sums per
  * item (shared doublings vs. parallelism).  0 (default) = chosen per call from the batch shape. */
 int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups);

@@ -66,7 +66,9 @@ def check_all(E, O, n_sig=6, n_comb=3, t=3, deg=6, n_eval=5, seed=7):
     """Every C-ABI entry point of engine E against the oracle on the same inputs (bit-exact)."""
     sk, pk, sig, msgs = make_sig_batch(O, n_sig, seed)
     h = O.hash_g2_batch(msgs)
-    assert np.array_equal(E.hash_g2_batch(msgs), h)
+    for algo in (1, 0):                                                        # one-kernel version, then the default two-kernel one
+        E.set_hash_algo(algo)
+        assert np.array_equal(E.hash_g2_batch(msgs), h), algo
     assert np.array_equal(E.g1_mul_gen_batch(sk), O.g1_mul_gen_batch(sk))
     long_msgs = [m * (1 + 9 * (k % 2)) for k, m in enumerate(msgs)]          # some > 64 bytes (hashed first), some short
     exp_hg = np.stack([O.hash_g1_g2(pk[k], long_msgs[k]) for k in range(n_sig)])
@@ -76,6 +78,7 @@ def check_all(E, O, n_sig=6, n_comb=3, t=3, deg=6, n_eval=5, seed=7):
     exp = O.verify_batch(pk, sig, msgs)
     assert 0 < exp.sum() < n_sig or n_sig < 3
     assert np.array_equal(E.verify_batch(pk, sig, msgs), exp)
+    check_verify_hash_modes(E, O, pk, sig, msgs, exp)
     assert np.array_equal(E.verify_g2_batch(pk, h, None, sig), O.verify_g2_batch(pk, h, None, sig))
     g1 = np.tile(O.g1_generator(), (n_sig, 1))
     assert np.array_equal(E.verify_g2_batch(pk, h, g1, sig), exp)
@@ -111,6 +114,22 @@ def check_all(E, O, n_sig=6, n_comb=3, t=3, deg=6, n_eval=5, seed=7):
     out = E.commitment_eval_batch(comm, xs)
     assert np.array_equal(out, O.commitment_eval_batch(comm, xs))
     assert np.array_equal(out, O.g1_mul_gen_batch(O.poly_eval(coeff, xs)))
+
+
+def check_verify_hash_modes(E, O, pk, sig, msgs, exp):
+    """PublicKey::verify with the message point taken up to the unit 3(x^2-1) and the generator scaled by the same unit
+    (the default, tcb200.h: tcb_set_verify_hash) must give the booleans of the exact-hash check — also for a wrong message,
+    a wrong key and a signature at infinity."""
+    n = len(msgs)
+    inf2 = np.zeros(192, np.uint8); inf2[0] = 0x40
+    sig_i = sig.copy(); sig_i[0] = inf2
+    trials = [(pk, sig, msgs), (pk, sig, msgs[1:] + msgs[:1]), (np.roll(pk, 1, axis=0), sig, msgs), (pk, sig_i, msgs)]
+    for k, (p_, s_, m_) in enumerate(trials):
+        want = exp if k == 0 else O.verify_batch(p_, s_, m_)
+        for mode, algo in ((1, 1), (0, 1), (1, 0), (0, 0)):
+            E.set_verify_hash(mode)
+            E.set_hash_algo(algo)
+            assert np.array_equal(E.verify_batch(p_, s_, m_), want), (k, mode, algo)
 
 
 def check_poly(E, O, seed=13):

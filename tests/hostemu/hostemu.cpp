@@ -25,16 +25,33 @@ extern "C" int tcb_verify_g2_batch(tcb_ctx *, size_t n, const u8 *a, const u8 *b
     for (size_t i = 0; i < n; i++) task_verify_g2<Fp2>(i, a, b, c, d, ok);
     return 0;
 }
+static int g_hash_algo = 0;
+extern "C" int tcb_set_hash_algo(tcb_ctx *, int a) { g_hash_algo = a; return 0; }
+// the two-kernel composition of tcb200.cu: point per item, cofactor clearing, one-kernel pass over the flagged items
+static void emu_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out, bool exact) {
+    if (g_hash_algo == 1) { for (size_t i = 0; i < n; i++) task_hash_g2<Fp2>(i, msgs, off, out, exact); return; }
+    std::vector<G2PointStore> pts(n + 1);
+    std::vector<u8> redo(n);
+    for (size_t i = 0; i < n; i++) task_hash_g2_point(i, msgs, off, &pts[i]);
+    for (size_t i = 0; i < n; i++) task_g2_clear<Fp2>(i, pts.data(), out, exact, redo.data());
+    for (size_t i = 0; i < n; i++) task_hash_g2<Fp2>(i, msgs, off, out, exact, redo.data());
+}
 extern "C" int tcb_hash_g2_batch(tcb_ctx *, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
-    for (size_t i = 0; i < n; i++) task_hash_g2<Fp2>(i, msgs, off, out);
+    emu_hash_g2(n, msgs, off, out, true);
     return 0;
 }
 extern "C" int tcb_hash_g1_g2_batch(tcb_ctx *, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
     for (size_t i = 0; i < n; i++) task_hash_g1_g2<Fp2>(i, g1, msgs, off, out);
     return 0;
 }
+static bool g_verify_exact = false;
+extern "C" int tcb_set_verify_hash(tcb_ctx *, int exact) { g_verify_exact = exact != 0; return 0; }
 extern "C" int tcb_verify_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
-    for (size_t i = 0; i < n; i++) task_verify<Fp2>(i, pk, sig, msgs, off, ok);
+    // as tcb200.cu: message points (exact, or up to the unit 3 (x^2 - 1)) into scratch, then the pairing check against the
+    // generator (or its multiple by the same unit)
+    std::vector<u8> h(192 * n);
+    emu_hash_g2(n, msgs, off, h.data(), g_verify_exact);
+    for (size_t i = 0; i < n; i++) task_verify_g2<Fp2>(i, pk, h.data(), nullptr, sig, ok, !g_verify_exact);
     return 0;
 }
 extern "C" int tcb_sign_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, u8 *out) {

@@ -263,6 +263,29 @@ def test_both_pairing_engines_vs_oracle(gpu_engine, O):
         E.set_engine(ENGINE_QUAD_SMEM)
 
 
+def test_hash_g2_algorithms_and_verify_modes(gpu_engine, O):
+    """tcb_set_hash_algo / tcb_set_verify_hash: the two-kernel hash_g2 (point per thread + cofactor clearing on lane pairs) and the
+    one-kernel version give the oracle's points on ragged messages (0..300 bytes, a count that leaves a partial warp), and
+    PublicKey::verify with the message point taken up to the unit 3(x^2-1) against the scaled generator gives the oracle's booleans
+    (valid, wrong message, wrong key, signature at infinity)."""
+    E = gpu_engine
+    O.set_threads(16)
+    n = 333
+    rng = np.random.default_rng(77)
+    msgs = [bytes(rng.integers(0, 256, int(l), dtype=np.uint8)) for l in rng.integers(0, 301, n)]
+    msgs[0] = b""; msgs[1] = bytes(135); msgs[2] = bytes(136); msgs[3] = bytes(137)
+    exp = O.hash_g2_batch(msgs)
+    try:
+        for algo in (1, 0):
+            E.set_hash_algo(algo)
+            assert np.array_equal(E.hash_g2_batch(msgs), exp), algo
+        sk, pk, sig, vm = cases.make_sig_batch(O, 200, 93, corrupt_every=5)
+        cases.check_verify_hash_modes(E, O, pk, sig, vm, O.verify_batch(pk, sig, vm))
+    finally:
+        E.set_hash_algo(0); E.set_verify_hash(0)
+        O.set_threads(1)
+
+
 def _poly_shares(coeff_bytes, xs_ints):
     """host big-int Horner: f(x) for every x (canonical 32-byte little-endian scalars)"""
     from conftest import R

@@ -89,6 +89,15 @@ class Engine:
     def set_engine(self, engine):
         self._ck(self.lib.tcb_set_engine(self.ctx, int(engine)))
 
+    def set_verify_hash(self, exact):
+        """verify_batch: 0 (default) pairs [3(x^2-1)]H(m) with [3(x^2-1)]g1 (the hash kernel skips the last third of the cofactor
+        clearing), 1 the exact H(m) with g1.  Same booleans."""
+        self._ck(self.lib.tcb_set_verify_hash(self.ctx, int(exact)))
+
+    def set_hash_algo(self, algo):
+        """hash_g2: 0 (default) point kernel (one thread per item) + cofactor-clearing kernel (lane pairs), 1 the one-kernel version."""
+        self._ck(self.lib.tcb_set_hash_algo(self.ctx, int(algo)))
+
     def set_msm_groups(self, groups):
         """Partial sums per item of the shared-doubling multi-scalar multiplication (0 = auto)."""
         self._ck(self.lib.tcb_set_msm_groups(self.ctx, C.c_size_t(int(groups))))

@@ -67,6 +67,13 @@ __global__ void __launch_bounds__(128) k_decrypt_finish(size_t n, size_t m, cons
     else { bool ok = true; g = load_g1(first_shares + 96 * i, ok); }
     xor_with_hash(out + voff[i], g, v + voff[i], (size_t)(voff[i + 1] - voff[i]));
 }
+// first half of the two-kernel hash_g2 (scheme.cuh: g2_random_point): SHA3, ChaCha, candidate search and the square root, one
+// THREAD per item; tail lanes recompute the last item so that whole warps stay alive for the __syncwarp() after the rejection loop
+__global__ void __launch_bounds__(128, 4) k_hash_g2_point(size_t n, const u8 *msgs, const u64 *off, G2PointStore *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < n;
+    task_hash_g2_point(live ? i : n - 1, msgs, off, out + (live ? i : n));      // record n absorbs the tail lanes
+}
 __global__ void __launch_bounds__(128) k_g1_decode(size_t n, const u8 *pts, Aff1Store *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) task_g1_decode(i, pts, out);
@@ -210,6 +217,9 @@ void run_g1_sum(cudaStream_t st, size_t n, size_t m, const void *terms, u8 *out)
 }
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out) {
     if (n) k_decrypt_finish<<<grid1(n), 128, 0, st>>>(n, m, (const Jac1Store *)terms, first_shares, v, voff, out);
+}
+void run_hash_g2_point(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, void *pts) {   // pts: n + 1 records (the last one absorbs the tail lanes)
+    if (n) k_hash_g2_point<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, msgs, off, (G2PointStore *)pts);
 }
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab) {
     if (n) k_g1_decode<<<grid1(n), 128, 0, st>>>(n, pts, (Aff1Store *)tab);

@@ -14,9 +14,14 @@ typedef Fp2S F2;
 #endif
 
 static __device__ __forceinline__ size_t unit_index() { return ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1; }
-__global__ void __launch_bounds__(128, TCB_G2_MINB) k_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out) {
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_hash_g2(size_t n, const u8 *msgs, const u64 *off, u8 *out, int exact, const u8 *only) {
     size_t i = unit_index();
-    if (i < n) task_hash_g2<F2>(i, msgs, off, out);
+    if (i < n) task_hash_g2<F2>(i, msgs, off, out, exact != 0, only);
+}
+// second half of the two-kernel hash_g2 (scheme.cuh: g2_random_point / task_g2_clear): cofactor clearing of the curve points
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_clear(size_t n, const G2PointStore *pts, u8 *out, int exact, u8 *redo) {
+    size_t i = unit_index();
+    if (i < n) task_g2_clear<F2>(i, pts, out, exact != 0, redo);
 }
 __global__ void __launch_bounds__(128, TCB_G2_MINB) k_hash_g1_g2(size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
     size_t i = unit_index();
@@ -71,8 +76,12 @@ cudaError_t upload_consts_g2(const Consts &c) {
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(d_consts, &c, sizeof c);
 }
-void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
-    if (n) k_hash_g2<<<grid2(n), 128, 0, st>>>(n, msgs, off, out);
+void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out, bool exact, const u8 *only) {
+    if (n) k_hash_g2<<<grid2(n), 128, 0, st>>>(n, msgs, off, out, exact ? 1 : 0, only);
+}
+size_t g2_point_bytes() { return sizeof(G2PointStore); }
+void run_g2_clear(cudaStream_t st, size_t n, const void *pts, u8 *out, bool exact, u8 *redo) {
+    if (n) k_g2_clear<<<grid2(n), 128, 0, st>>>(n, (const G2PointStore *)pts, out, exact ? 1 : 0, redo);
 }
 void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
     if (n) k_hash_g1_g2<<<grid2(n), 128, 0, st>>>(n, g1, msgs, off, out);

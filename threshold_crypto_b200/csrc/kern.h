@@ -24,10 +24,12 @@ void run_count_diff(cudaStream_t st, size_t bytes, const void *x, const void *y,
 // ---- k_miller.cu  (shared-memory engine: operands staged in shared memory, dot-product form)
 cudaError_t upload_consts_miller(const tcb::Consts &c);
 size_t miller_f_bytes();         // bytes of one Miller-loop value in the scratch buffer between the two kernels
-void run_miller_quad(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, void *fbuf, u8 *enc_ok);
+void run_miller_quad(cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, void *fbuf, u8 *enc_ok, bool gen_scaled = false);   // c == nullptr: the G1 generator, or [3 (x^2 - 1)] times it
 // ---- k_g2.cu  (lane-pair engine)
 cudaError_t upload_consts_g2(const tcb::Consts &c);
-void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out);
+void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out, bool exact = true, const u8 *only = nullptr);   // exact == false: [3 (x^2 - 1)] H(m) (verify only); only != nullptr: just the flagged items
+size_t g2_point_bytes();         // two-kernel hash_g2: curve point per item between run_hash_g2_point (k_g1.cu, one thread per item) and run_g2_clear
+void run_g2_clear(cudaStream_t st, size_t n, const void *pts, u8 *out, bool exact, u8 *redo);
 void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out);
 void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out);
 void run_g2_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out);
@@ -68,6 +70,7 @@ size_t g1_msm_ba_point_bytes(size_t cnt_max);
 size_t g1_msm_ba_prefix_bytes(size_t cnt_max);
 void run_g1_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *buf_a, void *buf_b, void *prefix, size_t cnt_max, void *out);
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
+void run_hash_g2_point(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, void *pts);
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);
 size_t commit_eval_units_per_sm();

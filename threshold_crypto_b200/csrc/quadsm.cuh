@@ -378,7 +378,7 @@ static_assert(QStage::END <= 3 * 3 * QNT * 16, "staging area fits the first thre
 
 // The Miller loop of e(a,b) * e(-c,d) for the block's 32 items; f goes to fout[(item * 4 + lane) * 3 + k], the encoding flag
 // (all field elements < p) to enc_ok[item].
-TCB_D void q_miller_block(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, Fp *fout, u8 *enc_ok) {
+TCB_D void q_miller_block(size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, Fp *fout, u8 *enc_ok, bool gen_scaled = false) {
     const u32 t = q_tid();
     const size_t first = (size_t)blockIdx.x * (QNT / 4);
     const u32 cnt = (u32)((n - first) < (size_t)(QNT / 4) ? (n - first) : (size_t)(QNT / 4));
@@ -424,7 +424,7 @@ TCB_D void q_miller_block(size_t n, const u8 *a, const u8 *b, const u8 *c, const
         pcoord = pinf ? Fp::zero() : q_load_be_sm(pg + (e ? 48 : 0), ok);
     } else {
         pinf = false;
-        pcoord = e ? CONSTS().g1y : CONSTS().g1x;
+        pcoord = gen_scaled ? (e ? CONSTS().g1cy : CONSTS().g1cx) : (e ? CONSTS().g1y : CONSTS().g1x);
     }
     if (!p0 && e) pcoord = -pcoord;                    // -C
     if (!qinf) { qx = q_load_be_sm(qg + (e ? 0 : 48), ok); qy = q_load_be_sm(qg + 96 + (e ? 0 : 48), ok); }

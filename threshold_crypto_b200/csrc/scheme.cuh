@@ -290,7 +290,7 @@ TCB_HD bool bcast_flag(bool v, int src) {
 //   * the cofactor multiplication runs AFTER the rejection loop (all lanes converged) and uses
 //     the psi-endomorphism identity of g2_clear_cofactor.
 template <class F2>
-TCB_HDN Jac<F2> g2_random(ChaChaRng &g) {
+TCB_HDN Jac<F2> g2_random(ChaChaRng &g, bool exact = true) {
     const Consts &C = CONSTS();
     constexpr int L = F2::SLICED ? 2 : 1;
     const int me = (int)my_role<F2>();
@@ -343,17 +343,78 @@ TCB_HDN Jac<F2> g2_random(ChaChaRng &g) {
         bool pick_y = (fp2_cmp(y, ny) < 0) != greatest;
         Aff<F2> pt;
         pt.x = F2::from_halves(x.c0, x.c1); pt.y = select(pick_y, y, ny); pt.inf = false;
-        Jac<F2> p = g2_clear_cofactor(pt);
+        Jac<F2> p = g2_clear_cofactor(pt, exact);
         if (!jac_is_inf(p)) return p;
     }
 }
 template <class F2>
-TCB_HD Jac<F2> hash_g2(const u8 *m1, size_t l1, const u8 *m2, size_t l2) {   // src/lib.rs:691-694
+TCB_HD Jac<F2> hash_g2(const u8 *m1, size_t l1, const u8 *m2, size_t l2, bool exact = true) {   // src/lib.rs:691-694
     u8 digest[32];
     sha3_256(m1, l1, m2, l2, digest);
     ChaChaRng g;
     rng_seed(g, digest);
-    return g2_random<F2>(g);
+    return g2_random<F2>(g, exact);
+}
+// ---- hash_g2 in two kernels.  Everything up to the curve point (SHA3, ChaCha, the candidate search, the two Fp powers of the
+// square root) is Fp-level work with nothing for the second lane of a pair to do — inside the lane-pair kernel both powers ran
+// redundantly on the two lanes.  g2_random_point is that first half for ONE thread per item (the residuosity of (a0 + s)/2 is
+// decided by a Legendre symbol, so exactly two powers per hash); task_g2_clear is the second half on the item's Fp2 engine.
+// The reference retries with further candidates when the cleared point is the identity (probability ~2^-255): such an item is
+// flagged in `redo` and recomputed by the one-kernel path (k_hash_g2 with its `only` filter), which continues the ChaCha stream.
+TCB_HDN void g2_random_point(ChaChaRng &g, Fp2 &px, Fp2 &py) {
+    const Consts &C = CONSTS();
+    Fp2 b2;
+    b2.c0 = C.b1; b2.c1 = C.b1;   // 4 (1 + u)
+    for (;;) {
+        Fp2 x, a;
+        Fp nrm;
+        bool greatest;
+        for (;;) {                                   // the rejection loop holds only the cheap part; lanes leave it at different trips
+            x.c0 = fp_random(g);
+            x.c1 = fp_random(g);
+            greatest = (rng_u32(g) & 1u) != 0;
+            a = sqr(x) * x + b2;
+            nrm = norm(a);
+            if (fp_is_square(nrm)) break;            // a is a square in Fp2 iff its norm is one in Fp
+        }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();                                // the kernel keeps all 32 lanes alive: the powers below run converged
+#endif
+        Fp2 y;
+        if (a.c1.is_zero()) {
+            fp2_sqrt(y, a);                          // a in Fp: generic Algorithm 9 (never hit by random x)
+        } else {
+            Fp s = fp_pow<ExpPp1d4>(nrm);            // sqrt(norm)
+            Fp d = fp_half(a.c0 + s);                // exactly one of (a0 + s)/2, (a0 - s)/2 is a square (their product is -a1^2/4)
+            if (!fp_is_square(d)) d = fp_half(a.c0 - s);
+            Fp e = fp_pow<ExpPm3d4>(d);              // y0 = d e = sqrt(d), 1/y0 = e
+            y.c0 = d * e;
+            y.c1 = fp_half(a.c1 * e);
+        }
+        Fp2 ny = -y;
+        bool pick_y = (fp2_cmp(y, ny) < 0) != greatest;
+        px = x; py = pick_y ? y : ny;
+        return;
+    }
+}
+struct G2PointStore { Fp2c x, y; };      // affine twist point, Montgomery limbs (scratch between the two kernels)
+TCB_HD void task_hash_g2_point(size_t i, const u8 *msgs, const u64 *off, G2PointStore *dst) {   // dst: where item i's point goes
+    u8 digest[32];
+    sha3_256(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0, digest);
+    ChaChaRng g;
+    rng_seed(g, digest);
+    Fp2 x, y;
+    g2_random_point(g, x, y);
+    x.store(dst->x); y.store(dst->y);
+}
+template <class F2>
+TCB_HD void task_g2_clear(size_t i, const G2PointStore *pts, u8 *out_g2, bool exact, u8 *redo) {
+    Aff<F2> pt;
+    pt.x = F2::load(pts[i].x); pt.y = F2::load(pts[i].y); pt.inf = false;
+    Jac<F2> p = g2_clear_cofactor(pt, exact);
+    bool inf = jac_is_inf(p);
+    if (is_writer<F2>()) redo[i] = inf ? 1 : 0;
+    if (!inf) store_g2<F2>(out_g2 + 192 * i, jac_to_aff(p));
 }
 template <class F2>
 TCB_HD Jac<F2> hash_g1_g2(const Aff<Fp> &g1, const u8 *msg, size_t len) {   // src/lib.rs:697-707
@@ -473,21 +534,22 @@ TCB_HD void task_poly_mul(size_t u, size_t da, size_t db, const Fr *am, const Fr
 // ----------------------------------------------------------------------------- per-item tasks
 // a1: e(a,b) == e(c,d); c == nullptr means the G1 generator (src/lib.rs:108-110,182-186,508-512)
 template <class F2>
-TCB_HD void task_verify_g2(size_t i, const u8 *a_g1, const u8 *b_g2, const u8 *c_g1, const u8 *d_g2, u8 *ok_out) {
+TCB_HD void task_verify_g2(size_t i, const u8 *a_g1, const u8 *b_g2, const u8 *c_g1, const u8 *d_g2, u8 *ok_out, bool gen_scaled = false) {
     bool ok = true;
     Aff<Fp> a = load_g1(a_g1 + 96 * i, ok);
     Aff<F2> b = load_g2<F2>(b_g2 + 192 * i, ok);
     Aff<Fp> c;
     if (c_g1) c = load_g1(c_g1 + 96 * i, ok);
-    else { c.x = CONSTS().g1x; c.y = CONSTS().g1y; c.inf = false; }
+    else { c.x = gen_scaled ? CONSTS().g1cx : CONSTS().g1x; c.y = gen_scaled ? CONSTS().g1cy : CONSTS().g1y; c.inf = false; }
     Aff<F2> d = load_g2<F2>(d_g2 + 192 * i, ok);
     bool res = pairing_eq<F2>(a, b, c, d);
     if (is_writer<F2>()) ok_out[i] = (res && ok) ? 1 : 0;
 }
 // a2: hash_g2 -> uncompressed affine G2
 template <class F2>
-TCB_HD void task_hash_g2(size_t i, const u8 *msgs, const u64 *off, u8 *out_g2) {
-    Jac<F2> h = hash_g2<F2>(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0);
+TCB_HD void task_hash_g2(size_t i, const u8 *msgs, const u64 *off, u8 *out_g2, bool exact = true, const u8 *only = nullptr) {   // exact == false: [3 (x^2 - 1)] H(m), see g2_clear_cofactor
+    if (only && !only[i]) return;            // second pass of the two-kernel path: only the flagged items
+    Jac<F2> h = hash_g2<F2>(msgs + off[i], (size_t)(off[i + 1] - off[i]), msgs, 0, exact);
     store_g2<F2>(out_g2 + 192 * i, jac_to_aff(h));
 }
 // a2: hash_g1_g2 (src/lib.rs:697-707) -> uncompressed affine G2
@@ -1126,6 +1188,12 @@ inline void build_consts(Consts &C) {
         Aff<Fp> m = jac_to_aff(jac_mul_aff<Fp, 8>(G, mu));       // [x^2] G = -phi(G)
         if (!(m.x == G.x * beta)) beta = sqr(beta);
         C.beta = beta;
+        u32 c3[8];                                               // 3 (x^2 - 1) < 2^130
+        u64 cy = 0, bw = 1;
+        for (int i = 0; i < 8; i++) { u64 d = (u64)mu[i] - bw; c3[i] = (u32)d; bw = (d >> 63) & 1; }
+        for (int i = 0; i < 8; i++) { u64 v = 3ull * c3[i] + cy; c3[i] = (u32)v; cy = v >> 32; }
+        Aff<Fp> gc = jac_to_aff(jac_mul_aff<Fp, 8>(G, c3));
+        C.g1cx = gc.x; C.g1cy = gc.y;
     }
     h_consts = C;
 }

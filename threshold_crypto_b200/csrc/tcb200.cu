@@ -52,6 +52,8 @@ struct tcb_ctx {
     size_t msm_groups = 0;          // 0 = auto (pick_groups)
     size_t eval_split = 0;          // units per point of Commitment::evaluate: 0 = auto (tcb_set_eval_split)
     bool eval_split_off = false;
+    bool verify_exact_hash = false; // tcb_set_verify_hash
+    bool hash_fused = false;        // tcb_set_hash_algo: the one-kernel hash_g2 (round 1/2a) instead of point + clearing kernels
     int msm_algo = 0;               // MSM_STRAUS (default) | MSM_BATCH_AFFINE | MSM_PER_SHARE (tcb_set_msm_algo; the others are measurement knobs)
 };
 
@@ -106,29 +108,41 @@ static void *arena_alloc(tcb_ctx *ctx, DevState &d, size_t bytes) {
     } while (0)
 
 // ----------------------------------------------------------------------------- device-side implementations
-static int impl_verify_g2(tcb_ctx *ctx, DevState &dv, cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok) {
+static int impl_verify_g2(tcb_ctx *ctx, DevState &dv, cudaStream_t st, size_t n, const u8 *a, const u8 *b, const u8 *c, const u8 *d, u8 *ok, bool gen_scaled = false) {
     if (!n) return 0;
-    if (ctx->engine == TCB_ENGINE_QUAD_REG) { RUN(run_verify_g2_quad(st, n, a, b, c, d, ok)); return 0; }
+    if (ctx->engine == TCB_ENGINE_QUAD_REG) { RUN(run_verify_g2_quad(st, n, a, b, c, d, ok)); return 0; }   // callers never ask this engine for gen_scaled
     // Miller loop (shared-memory engine) -> f, 576 B per item in scratch -> final exponentiation and "== 1"
     void *fbuf = arena_alloc(ctx, dv, n * miller_f_bytes());
     u8 *enc = (u8 *)arena_alloc(ctx, dv, n);
     if (!fbuf || !enc) return -1;
-    RUN(run_miller_quad(st, n, a, b, c, d, fbuf, enc));
+    RUN(run_miller_quad(st, n, a, b, c, d, fbuf, enc, gen_scaled));
     if (ctx->engine == TCB_ENGINE_QUAD_SMEM_REGFE) RUN(run_final_exp_quad(st, n, fbuf, enc, ok, nullptr));
     else RUN(run_final_exp_sm(st, n, fbuf, enc, ok, nullptr));
     return 0;
 }
-static int impl_hash_g2(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
-    if (n) RUN(run_hash_g2(st, n, msgs, off, out));
+// hash_g2 (exact) or, for the verifier, [3 (x^2 - 1)] hash_g2.  Default: two kernels — the curve point with one thread per item
+// (k_hash_g2_point), the cofactor clearing on lane pairs (k_g2_clear) — and a pass of the one-kernel version over the items whose
+// cleared point was the identity (the reference draws further candidates then; probability ~2^-255, the launch is ~free).
+static int impl_hash_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out, bool exact = true) {
+    if (!n) return 0;
+    if (ctx->hash_fused) { RUN(run_hash_g2(st, n, msgs, off, out, exact)); return 0; }
+    void *pts = arena_alloc(ctx, d, (n + 1) * g2_point_bytes());
+    u8 *redo = (u8 *)arena_alloc(ctx, d, n);
+    if (!pts || !redo) return -1;
+    RUN(run_hash_g2_point(st, n, msgs, off, pts));
+    RUN(run_g2_clear(st, n, pts, out, exact, redo));
+    RUN(run_hash_g2(st, n, msgs, off, out, exact, redo));
     return 0;
 }
 static int impl_verify(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     if (!n) return 0;
-    // hash_g2 on lane pairs into scratch, then the quad pairing check e(pk, H) == e(g1, sig)
+    // hash_g2 on lane pairs into scratch, then the quad pairing check e(pk, H) == e(g1, sig) — by default as
+    // e(pk, cH) == e(c g1, sig) with c = 3 (x^2 - 1): the hash kernel skips the last third of the cofactor clearing (tcb200.h)
     u8 *h = (u8 *)arena_alloc(ctx, d, n * 192);
     if (!h) return -1;
-    RUN(run_hash_g2(st, n, msgs, off, h));
-    return impl_verify_g2(ctx, d, st, n, pk, h, nullptr, sig, ok);
+    const bool scaled = !ctx->verify_exact_hash && ctx->engine != TCB_ENGINE_QUAD_REG;
+    if (impl_hash_g2(ctx, d, st, n, msgs, off, h, !scaled)) return -1;
+    return impl_verify_g2(ctx, d, st, n, pk, h, nullptr, sig, ok, scaled);
 }
 static int impl_sign(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     if (n) RUN(run_sign(st, n, sk, msgs, off, h, out));
@@ -328,6 +342,16 @@ extern "C" int tcb_set_engine(tcb_ctx *ctx, int engine) {
     ctx->engine = engine;
     return 0;
 }
+extern "C" int tcb_set_verify_hash(tcb_ctx *ctx, int exact) {
+    if (!ctx) return -2;
+    ctx->verify_exact_hash = exact != 0;
+    return 0;
+}
+extern "C" int tcb_set_hash_algo(tcb_ctx *ctx, int algo) {
+    if (!ctx || algo < 0 || algo > 1) return -2;
+    ctx->hash_fused = algo == 1;
+    return 0;
+}
 extern "C" int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups) {
     if (!ctx) return -2;
     ctx->msm_groups = groups;
@@ -388,7 +412,7 @@ extern "C" int tcb_final_exp_is_one_batch_dev(tcb_ctx *ctx, void *stream, size_t
 extern "C" size_t tcb_miller_value_bytes(void) { return miller_f_bytes(); }
 extern "C" int tcb_hash_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     DEV_PROLOGUE
-    DEV_RETURN(impl_hash_g2(ctx, st, n, msgs, off, out));
+    DEV_RETURN(impl_hash_g2(ctx, d, st, n, msgs, off, out));
 }
 extern "C" int tcb_verify_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     DEV_PROLOGUE
@@ -534,7 +558,7 @@ extern "C" int tcb_hash_g2_batch(tcb_ctx *ctx, size_t n, const u8 *msgs, const u
         if (up_msgs(ctx, d, msgs, off, s.lo, s.hi, keep, dm, doff)) return -1;
         u8 *dout = (u8 *)arena_alloc(ctx, d, 192 * cnt);
         if (!dout) return -1;
-        if (impl_hash_g2(ctx, st, cnt, dm, doff, dout)) return -1;
+        if (impl_hash_g2(ctx, d, st, cnt, dm, doff, dout)) return -1;
         if (down(ctx, d, out + 192 * s.lo, dout, 192 * cnt)) return -1;
     END_FOR_EACH_DEV
     return sync_all(ctx);

@@ -30,6 +30,7 @@ struct Consts {
     Fp2c psi_x, psi_y;  // untwist-Frobenius-twist endomorphism: psi(x,y) = (conj(x) psi_x, conj(y) psi_y)
     Fp2c psi_cx[4], psi_cy[4];   // psi^i(x,y) = (conj^i(x) psi_cx[i], conj^i(y) psi_cy[i])
     Fp beta;            // cube root of unity in Fp with (beta x, y) = [-x^2] (x, y) on G1
+    Fp g1cx, g1cy;      // [3 (x^2 - 1)] G1 generator: partner of the h_eff-cleared message point inside PublicKey::verify (g2_clear_cofactor)
 };
 #if defined(__CUDACC__)
 static __device__ __constant__ Consts d_consts;   // one copy per translation unit (uploaded by each)
@@ -948,10 +949,13 @@ TCB_HDN Jac<F> jac_mul_naf64(const Jac<F> &p, u64 plus, u64 minus) {
 //   [h2]P = [1/(3(x^2-1)) mod r] Q0,  and on G2 (psi = [x]):  1/(x^2-1) = -x^2,  1/3 = 1 + 2 x^2 (x+1) (x-1)/3
 //   => R = -psi^2(Q0),  T = psi^2(psi(R) + R),  [h2]P = R - [w] T,  w = 2(|x|+1)/3 = 0x8c00aaaaaaab5556.
 // Same group element as the reference's 507-bit double-and-add (checked against it in the tests).
+// exact == false stops at Q0 = [3 (x^2 - 1)] [h2]P: a verifier that only needs e(pk, H) == e(g1, sig) can test
+// e(pk, Q0) == e([3 (x^2 - 1)] g1, sig) instead (3 (x^2 - 1) is a unit mod r, so the two equalities are equivalent) and
+// skip the third 64-bit multiplication; [3 (x^2 - 1)] g1 is the constant Consts::g1cx/g1cy.
 #define TCB_W_PLUS 0x9001000000000000ULL
 #define TCB_W_MINUS 0x040055555554aaaaULL
 template <class F2>
-TCB_HDN Jac<F2> g2_clear_cofactor(const Aff<F2> &p) {
+TCB_HDN Jac<F2> g2_clear_cofactor(const Aff<F2> &p, bool exact = true) {
     const u64 X = TCB_BLS_X;
     Jac<F2> pj = jac_from_aff(p);
     Jac<F2> t1 = jac_neg(jac_mul_u64(pj, X));             // [x]P
@@ -963,6 +967,7 @@ TCB_HDN Jac<F2> g2_clear_cofactor(const Aff<F2> &p) {
     t3 = jac_add(t3, t2);
     t3 = jac_add(t3, jac_neg(t1));
     Jac<F2> q0 = jac_add(t3, jac_neg(pj));
+    if (!exact) return q0;
     Jac<F2> r = jac_neg(jac_psi(jac_psi(q0)));
     Jac<F2> t = jac_psi(jac_psi(jac_add(jac_psi(r), r)));
     return jac_add(r, jac_neg(jac_mul_naf64(t, TCB_W_PLUS, TCB_W_MINUS)));

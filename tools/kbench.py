@@ -20,11 +20,15 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "lib"
 which = set((sys.argv[2] if len(sys.argv) > 2 else "verify,combine,decrypt,eval,g1mul,sign").split(","))
 REPS = int(os.environ.get("REPS", "5"))
 E = Engine(devices=[0])
+if "HASH_ALGO" in os.environ:
+    E.set_hash_algo(int(os.environ["HASH_ALGO"]))
+if "VERIFY_HASH" in os.environ:
+    E.set_verify_hash(int(os.environ["VERIFY_HASH"]))
 dev = torch.device("cuda", 0)
 st = torch.cuda.current_stream().cuda_stream
 rng = np.random.default_rng(7)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-res = {"tag": tag, "lib": os.path.basename(E.path)}
+res = {"tag": tag, "lib": os.path.basename(E.path), "hash_algo": os.environ.get("HASH_ALGO", "default"), "verify_hash": os.environ.get("VERIFY_HASH", "default")}
 
 
 def D(a):
