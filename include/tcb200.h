@@ -152,6 +152,13 @@ int tcb_miller_loop_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *
                               const uint8_t *c_g1, const uint8_t *d_g2, void *f_out, uint8_t *enc_ok);
 int tcb_final_exp_is_one_batch_dev(tcb_ctx *, void *stream, size_t n, const void *f_in, const uint8_t *enc_ok, uint8_t *ok);
 size_t tcb_miller_value_bytes(void);
+/* The first step of tcb_verify_batch_dev on its own: the message points the verifier pairs with pk, i.e. (by default, see
+ * tcb_set_verify_hash) Q0_i = [3 (x^2 - 1)] hash_g2(msg_i), as uncompressed affine G2.  The matching first argument of the other
+ * pairing is tcb_verifier_generator (the 96-byte encoding of [3 (x^2 - 1)] g1, or of g1 after tcb_set_verify_hash(ctx, 1)):
+ *   tcb_verify_batch == tcb_verify_g2_batch(a = pk, b = these points, c = that generator for every item, d = sig).
+ * bench.py times the hash kernels of the verify step through this entry point. */
+int tcb_verifier_hash_g2_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *msgs, const uint64_t *off, uint8_t *out_g2);
+int tcb_verifier_generator(const tcb_ctx *, uint8_t *out_g1);
 int tcb_verify_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *pk_g1, const uint8_t *sig_g2,
                          const uint8_t *msgs, const uint64_t *off, uint8_t *ok);
 int tcb_sign_batch_dev(tcb_ctx *, void *stream, size_t n, const uint8_t *sk, const uint8_t *msgs,

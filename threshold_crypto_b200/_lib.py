@@ -111,6 +111,12 @@ class Engine:
         """Units per point of Commitment::evaluate: 0 auto, 1 never split, k forced."""
         self._ck(self.lib.tcb_set_eval_split(self.ctx, C.c_size_t(int(units))))
 
+    def verifier_generator(self):
+        """96-byte G1 point that verify_batch pairs with the signature: [3(x^2-1)] g1 by default, g1 after set_verify_hash(1)."""
+        out = np.zeros(96, np.uint8)
+        self._ck(self.lib.tcb_verifier_generator(self.ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def launch_count(self):
         return int(self.lib.tcb_launch_count(self.ctx))
 

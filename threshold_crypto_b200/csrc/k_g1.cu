@@ -74,6 +74,14 @@ __global__ void __launch_bounds__(128, 4) k_hash_g2_point(size_t n, const u8 *ms
     bool live = i < n;
     task_hash_g2_point(live ? i : n - 1, msgs, off, out + (live ? i : n));      // record n absorbs the tail lanes
 }
+// experiment (tcb_set_hash_algo 2): the cofactor clearing with one THREAD per item as well (unsliced Fp2, no lane exchanges)
+#ifndef TCB_CLEAR_THREAD_MINB
+#define TCB_CLEAR_THREAD_MINB 2
+#endif
+__global__ void __launch_bounds__(128, TCB_CLEAR_THREAD_MINB) k_g2_clear_thread(size_t n, const G2PointStore *pts, u8 *out, int exact, u8 *redo) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) task_g2_clear<Fp2>(i, pts, out, exact != 0, redo);
+}
 __global__ void __launch_bounds__(128) k_g1_decode(size_t n, const u8 *pts, Aff1Store *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) task_g1_decode(i, pts, out);
@@ -220,6 +228,9 @@ void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, 
 }
 void run_hash_g2_point(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, void *pts) {   // pts: n + 1 records (the last one absorbs the tail lanes)
     if (n) k_hash_g2_point<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, msgs, off, (G2PointStore *)pts);
+}
+void run_g2_clear_thread(cudaStream_t st, size_t n, const void *pts, u8 *out, bool exact, u8 *redo) {
+    if (n) k_g2_clear_thread<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, (const G2PointStore *)pts, out, exact ? 1 : 0, redo);
 }
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab) {
     if (n) k_g1_decode<<<grid1(n), 128, 0, st>>>(n, pts, (Aff1Store *)tab);

@@ -53,7 +53,7 @@ struct tcb_ctx {
     size_t eval_split = 0;          // units per point of Commitment::evaluate: 0 = auto (tcb_set_eval_split)
     bool eval_split_off = false;
     bool verify_exact_hash = false; // tcb_set_verify_hash
-    bool hash_fused = false;        // tcb_set_hash_algo: the one-kernel hash_g2 (round 1/2a) instead of point + clearing kernels
+    int hash_algo = 0;              // tcb_set_hash_algo: 0 point + clearing kernels, 1 the one-kernel hash_g2 (round 1/2a), 2 clearing per thread (experiment)
     int msm_algo = 0;               // MSM_STRAUS (default) | MSM_BATCH_AFFINE | MSM_PER_SHARE (tcb_set_msm_algo; the others are measurement knobs)
 };
 
@@ -125,12 +125,13 @@ static int impl_verify_g2(tcb_ctx *ctx, DevState &dv, cudaStream_t st, size_t n,
 // cleared point was the identity (the reference draws further candidates then; probability ~2^-255, the launch is ~free).
 static int impl_hash_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out, bool exact = true) {
     if (!n) return 0;
-    if (ctx->hash_fused) { RUN(run_hash_g2(st, n, msgs, off, out, exact)); return 0; }
+    if (ctx->hash_algo == 1) { RUN(run_hash_g2(st, n, msgs, off, out, exact)); return 0; }
     void *pts = arena_alloc(ctx, d, (n + 1) * g2_point_bytes());
     u8 *redo = (u8 *)arena_alloc(ctx, d, n);
     if (!pts || !redo) return -1;
     RUN(run_hash_g2_point(st, n, msgs, off, pts));
-    RUN(run_g2_clear(st, n, pts, out, exact, redo));
+    if (ctx->hash_algo == 2) RUN(run_g2_clear_thread(st, n, pts, out, exact, redo));
+    else RUN(run_g2_clear(st, n, pts, out, exact, redo));
     RUN(run_hash_g2(st, n, msgs, off, out, exact, redo));
     return 0;
 }
@@ -348,8 +349,8 @@ extern "C" int tcb_set_verify_hash(tcb_ctx *ctx, int exact) {
     return 0;
 }
 extern "C" int tcb_set_hash_algo(tcb_ctx *ctx, int algo) {
-    if (!ctx || algo < 0 || algo > 1) return -2;
-    ctx->hash_fused = algo == 1;
+    if (!ctx || algo < 0 || algo > 2) return -2;
+    ctx->hash_algo = algo;
     return 0;
 }
 extern "C" int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups) {
@@ -413,6 +414,18 @@ extern "C" size_t tcb_miller_value_bytes(void) { return miller_f_bytes(); }
 extern "C" int tcb_hash_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
     DEV_PROLOGUE
     DEV_RETURN(impl_hash_g2(ctx, d, st, n, msgs, off, out));
+}
+extern "C" int tcb_verifier_hash_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *msgs, const u64 *off, u8 *out) {
+    DEV_PROLOGUE
+    DEV_RETURN(impl_hash_g2(ctx, d, st, n, msgs, off, out, ctx->verify_exact_hash || ctx->engine == TCB_ENGINE_QUAD_REG));
+}
+extern "C" int tcb_verifier_generator(const tcb_ctx *ctx, u8 *out_g1) {
+    if (!ctx || !out_g1) return -2;
+    const bool scaled = !ctx->verify_exact_hash && ctx->engine != TCB_ENGINE_QUAD_REG;
+    Aff<Fp> g;
+    g.x = scaled ? h_consts.g1cx : h_consts.g1x; g.y = scaled ? h_consts.g1cy : h_consts.g1y; g.inf = false;
+    store_g1(out_g1, g);
+    return 0;
 }
 extern "C" int tcb_verify_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     DEV_PROLOGUE

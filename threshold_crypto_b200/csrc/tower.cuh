@@ -931,6 +931,18 @@ TCB_HDN Jac<F> jac_mul_u64(const Jac<F> &p, u64 k) {
     }
     return acc;
 }
+// the same for an affine base: every addition is a mixed addition
+template <class F>
+TCB_HDN Jac<F> jac_mul_u64_aff(const Aff<F> &p, u64 k) {
+    Jac<F> acc = jac_from_aff(p);
+    int top = 63;
+    while (top > 0 && !((k >> top) & 1)) top--;
+    for (int i = top - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        if ((k >> i) & 1) acc = jac_add_mixed(acc, p);
+    }
+    return acc;
+}
 // sum_j (plus_j - minus_j) 2^j * P, digits given as NAF bit masks
 template <class F>
 TCB_HDN Jac<F> jac_mul_naf64(const Jac<F> &p, u64 plus, u64 minus) {
@@ -958,7 +970,7 @@ template <class F2>
 TCB_HDN Jac<F2> g2_clear_cofactor(const Aff<F2> &p, bool exact = true) {
     const u64 X = TCB_BLS_X;
     Jac<F2> pj = jac_from_aff(p);
-    Jac<F2> t1 = jac_neg(jac_mul_u64(pj, X));             // [x]P
+    Jac<F2> t1 = jac_neg(jac_mul_u64_aff(p, X));          // [x]P
     Jac<F2> t2 = jac_psi(pj);
     Jac<F2> t3 = jac_psi(jac_psi(jac_dbl(pj)));
     t3 = jac_add(t3, jac_neg(t2));
