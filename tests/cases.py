@@ -72,8 +72,11 @@ def check_all(E, O, n_sig=6, n_comb=3, t=3, deg=6, n_eval=5, seed=7):
     assert np.array_equal(E.g1_mul_gen_batch(sk), O.g1_mul_gen_batch(sk))
     long_msgs = [m * (1 + 9 * (k % 2)) for k, m in enumerate(msgs)]          # some > 64 bytes (hashed first), some short
     exp_hg = np.stack([O.hash_g1_g2(pk[k], long_msgs[k]) for k in range(n_sig)])
-    assert np.array_equal(E.hash_g1_g2_batch(pk, long_msgs), exp_hg)
-    assert np.array_equal(E.sign_batch(sk, msgs), O.sign_batch(sk, msgs))
+    exp_sig = O.sign_batch(sk, msgs)
+    for algo in (1, 0):
+        E.set_hash_algo(algo)
+        assert np.array_equal(E.hash_g1_g2_batch(pk, long_msgs), exp_hg), algo
+        assert np.array_equal(E.sign_batch(sk, msgs), exp_sig), algo
     assert np.array_equal(E.sign_g2_batch(sk, h), O.sign_g2_batch(sk, h))
     exp = O.verify_batch(pk, sig, msgs)
     assert 0 < exp.sum() < n_sig or n_sig < 3
@@ -121,6 +124,10 @@ def check_verify_hash_modes(E, O, pk, sig, msgs, exp):
     (the default, tcb200.h: tcb_set_verify_hash) must give the booleans of the exact-hash check — also for a wrong message,
     a wrong key and a signature at infinity."""
     n = len(msgs)
+    X2 = 0xd201000000010000 ** 2
+    for mode, k in ((1, 1), (0, 3 * (X2 - 1))):              # the generator verify pairs with the signature: g1, or [3(x^2-1)] g1
+        E.set_verify_hash(mode)
+        assert np.array_equal(E.verifier_generator(), O.g1_mul_gen_batch(fr_bytes([k]))[0]), mode
     inf2 = np.zeros(192, np.uint8); inf2[0] = 0x40
     sig_i = sig.copy(); sig_i[0] = inf2
     trials = [(pk, sig, msgs), (pk, sig, msgs[1:] + msgs[:1]), (np.roll(pk, 1, axis=0), sig, msgs), (pk, sig_i, msgs)]

@@ -41,11 +41,23 @@ extern "C" int tcb_hash_g2_batch(tcb_ctx *, size_t n, const u8 *msgs, const u64 
     return 0;
 }
 extern "C" int tcb_hash_g1_g2_batch(tcb_ctx *, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
-    for (size_t i = 0; i < n; i++) task_hash_g1_g2<Fp2>(i, g1, msgs, off, out);
+    if (g_hash_algo == 1) { for (size_t i = 0; i < n; i++) task_hash_g1_g2<Fp2>(i, g1, msgs, off, out); return 0; }
+    std::vector<G2PointStore> pts(n + 1);
+    std::vector<u8> redo(n);
+    for (size_t i = 0; i < n; i++) task_hash_g1_g2_point(i, g1, msgs, off, &pts[i]);
+    for (size_t i = 0; i < n; i++) task_g2_clear<Fp2>(i, pts.data(), out, true, redo.data());
+    for (size_t i = 0; i < n; i++) task_hash_g1_g2<Fp2>(i, g1, msgs, off, out, redo.data());
     return 0;
 }
 static bool g_verify_exact = false;
 extern "C" int tcb_set_verify_hash(tcb_ctx *, int exact) { g_verify_exact = exact != 0; return 0; }
+extern "C" int tcb_verifier_generator(const tcb_ctx *, u8 *out_g1) {
+    ensure();
+    Aff<Fp> g;
+    g.x = g_verify_exact ? CONSTS().g1x : CONSTS().g1cx; g.y = g_verify_exact ? CONSTS().g1y : CONSTS().g1cy; g.inf = false;
+    store_g1(out_g1, g);
+    return 0;
+}
 extern "C" int tcb_verify_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *sig, const u8 *msgs, const u64 *off, u8 *ok) {
     // as tcb200.cu: message points (exact, or up to the unit 3 (x^2 - 1)) into scratch, then the pairing check against the
     // generator (or its multiple by the same unit)
@@ -55,7 +67,10 @@ extern "C" int tcb_verify_batch(tcb_ctx *, size_t n, const u8 *pk, const u8 *sig
     return 0;
 }
 extern "C" int tcb_sign_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, u8 *out) {
-    for (size_t i = 0; i < n; i++) task_sign<Fp2>(i, sk, msgs, off, nullptr, out);
+    if (g_hash_algo == 1) { for (size_t i = 0; i < n; i++) task_sign<Fp2>(i, sk, msgs, off, nullptr, out); return 0; }
+    std::vector<u8> h(192 * n);                       // as tcb200.cu: two-kernel hash into scratch, then the multiplication
+    emu_hash_g2(n, msgs, off, h.data(), true);
+    for (size_t i = 0; i < n; i++) task_sign<Fp2>(i, sk, nullptr, nullptr, h.data(), out);
     return 0;
 }
 extern "C" int tcb_sign_g2_batch(tcb_ctx *, size_t n, const u8 *sk, const u8 *h, u8 *out) {
@@ -312,8 +327,22 @@ extern "C" int tcb_emu_issquare_check(int n, uint64_t seed) {
         if (i == n + 2) a = -fp_one();          // -1 is a non-residue (p = 3 mod 4)
         Fp s = fp_pow<ExpPp1d4>(a);
         bool want = sqr(s) == a;
-        if (fp_is_square(a) != want) bad++;
+        if (fp_is_square(a) != want || fp_is_square_basic(a) != want) bad++;
         squares += want;
+    }
+    // values with long runs of trailing zeros (the production version removes up to 31 per iteration): +-2^k, 2^k * odd, low limbs zero
+    for (int k = 0; k < 381; k++) {
+        Fp pw = Fp::zero();
+        pw.l[k >> 5] = 1u << (k & 31);
+        if (!limbs_lt_mod<FpParams>(pw.l)) continue;
+        Fp cand[3] = {pw, -pw, pw};
+        for (int j = 0; j < 12; j++) if (j > (k >> 5)) { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; cand[2].l[j] = (u32)(seed >> 32); }
+        cand[2].l[11] &= 0x0fffffffu;
+        for (int c = 0; c < 3; c++) {
+            Fp s = fp_pow<ExpPp1d4>(cand[c]);
+            bool want = sqr(s) == cand[c];
+            if (fp_is_square(cand[c]) != want || fp_is_square_basic(cand[c]) != want) bad++;
+        }
     }
     return bad * 100000 + squares;
 }

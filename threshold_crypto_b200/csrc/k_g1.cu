@@ -74,6 +74,11 @@ __global__ void __launch_bounds__(128, 4) k_hash_g2_point(size_t n, const u8 *ms
     bool live = i < n;
     task_hash_g2_point(live ? i : n - 1, msgs, off, out + (live ? i : n));      // record n absorbs the tail lanes
 }
+__global__ void __launch_bounds__(128, 4) k_hash_g1_g2_point(size_t n, const u8 *g1, const u8 *msgs, const u64 *off, G2PointStore *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < n;
+    task_hash_g1_g2_point(live ? i : n - 1, g1, msgs, off, out + (live ? i : n));
+}
 // experiment (tcb_set_hash_algo 2): the cofactor clearing with one THREAD per item as well (unsliced Fp2, no lane exchanges)
 #ifndef TCB_CLEAR_THREAD_MINB
 #define TCB_CLEAR_THREAD_MINB 2
@@ -228,6 +233,9 @@ void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, 
 }
 void run_hash_g2_point(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, void *pts) {   // pts: n + 1 records (the last one absorbs the tail lanes)
     if (n) k_hash_g2_point<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, msgs, off, (G2PointStore *)pts);
+}
+void run_hash_g1_g2_point(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, void *pts) {
+    if (n) k_hash_g1_g2_point<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, g1, msgs, off, (G2PointStore *)pts);
 }
 void run_g2_clear_thread(cudaStream_t st, size_t n, const void *pts, u8 *out, bool exact, u8 *redo) {
     if (n) k_g2_clear_thread<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, (const G2PointStore *)pts, out, exact ? 1 : 0, redo);

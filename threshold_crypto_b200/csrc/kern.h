@@ -30,7 +30,7 @@ cudaError_t upload_consts_g2(const tcb::Consts &c);
 void run_hash_g2(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, u8 *out, bool exact = true, const u8 *only = nullptr);   // exact == false: [3 (x^2 - 1)] H(m) (verify only); only != nullptr: just the flagged items
 size_t g2_point_bytes();         // two-kernel hash_g2: curve point per item between run_hash_g2_point (k_g1.cu, one thread per item) and run_g2_clear
 void run_g2_clear(cudaStream_t st, size_t n, const void *pts, u8 *out, bool exact, u8 *redo);
-void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out);
+void run_hash_g1_g2(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out, const u8 *only = nullptr);
 void run_sign(cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out);
 void run_g2_compress(cudaStream_t st, size_t n, const u8 *unc, u8 *out);
 void run_g2_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *status);
@@ -71,6 +71,7 @@ size_t g1_msm_ba_prefix_bytes(size_t cnt_max);
 void run_g1_msm_acc_ba(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *buf_a, void *buf_b, void *prefix, size_t cnt_max, void *out);
 void run_decrypt_finish(cudaStream_t st, size_t n, size_t m, const void *terms, const u8 *first_shares, const u8 *v, const u64 *voff, u8 *out);
 void run_hash_g2_point(cudaStream_t st, size_t n, const u8 *msgs, const u64 *off, void *pts);
+void run_hash_g1_g2_point(cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, void *pts);
 void run_g2_clear_thread(cudaStream_t st, size_t n, const void *pts, u8 *out, bool exact, u8 *redo);
 void run_g1_decode(cudaStream_t st, size_t n, const u8 *pts, void *tab);
 void run_commit_eval(cudaStream_t st, size_t n, size_t deg, const void *tab, const u8 *x, u8 *out);

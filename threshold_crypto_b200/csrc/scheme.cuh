@@ -407,6 +407,26 @@ TCB_HD void task_hash_g2_point(size_t i, const u8 *msgs, const u64 *off, G2Point
     g2_random_point(g, x, y);
     x.store(dst->x); y.store(dst->y);
 }
+// the same first half for hash_g1_g2 (src/lib.rs:697-707): SHA3 over msg (or its digest when longer than 64 bytes) || compressed g1
+TCB_HD void task_hash_g1_g2_point(size_t i, const u8 *g1_pts, const u8 *msgs, const u64 *off, G2PointStore *dst) {
+    bool ok = true;
+    Aff<Fp> g1 = load_g1(g1_pts + 96 * i, ok);
+    const u8 *msg = msgs + off[i];
+    size_t len = (size_t)(off[i + 1] - off[i]);
+    u8 comp[48], d[32], digest[32];
+    g1_compress(comp, g1);
+    if (len > 64) {
+        sha3_256(msg, len, msg, 0, d);
+        sha3_256(d, 32, comp, 48, digest);
+    } else {
+        sha3_256(msg, len, comp, 48, digest);
+    }
+    ChaChaRng g;
+    rng_seed(g, digest);
+    Fp2 x, y;
+    g2_random_point(g, x, y);
+    x.store(dst->x); y.store(dst->y);
+}
 template <class F2>
 TCB_HD void task_g2_clear(size_t i, const G2PointStore *pts, u8 *out_g2, bool exact, u8 *redo) {
     Aff<F2> pt;
@@ -554,7 +574,8 @@ TCB_HD void task_hash_g2(size_t i, const u8 *msgs, const u64 *off, u8 *out_g2, b
 }
 // a2: hash_g1_g2 (src/lib.rs:697-707) -> uncompressed affine G2
 template <class F2>
-TCB_HD void task_hash_g1_g2(size_t i, const u8 *g1_pts, const u8 *msgs, const u64 *off, u8 *out_g2) {
+TCB_HD void task_hash_g1_g2(size_t i, const u8 *g1_pts, const u8 *msgs, const u64 *off, u8 *out_g2, const u8 *only = nullptr) {
+    if (only && !only[i]) return;            // second pass of the two-kernel path: only the flagged items
     bool ok = true;
     Aff<Fp> g = load_g1(g1_pts + 96 * i, ok);
     Jac<F2> h = hash_g1_g2<F2>(g, msgs + off[i], (size_t)(off[i + 1] - off[i]));

@@ -145,8 +145,29 @@ static int impl_verify(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, con
     if (impl_hash_g2(ctx, d, st, n, msgs, off, h, !scaled)) return -1;
     return impl_verify_g2(ctx, d, st, n, pk, h, nullptr, sig, ok, scaled);
 }
-static int impl_sign(tcb_ctx *ctx, cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
-    if (n) RUN(run_sign(st, n, sk, msgs, off, h, out));
+// hash_g1_g2 (src/lib.rs:697-707) the same way: point kernel with the compressed g1 in the SHA3 input, exact clearing, fallback pass
+static int impl_hash_g1_g2(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, const u8 *g1, const u8 *msgs, const u64 *off, u8 *out) {
+    if (!n) return 0;
+    if (ctx->hash_algo == 1) { RUN(run_hash_g1_g2(st, n, g1, msgs, off, out)); return 0; }
+    void *pts = arena_alloc(ctx, d, (n + 1) * g2_point_bytes());
+    u8 *redo = (u8 *)arena_alloc(ctx, d, n);
+    if (!pts || !redo) return -1;
+    RUN(run_hash_g1_g2_point(st, n, g1, msgs, off, pts));
+    if (ctx->hash_algo == 2) RUN(run_g2_clear_thread(st, n, pts, out, true, redo));
+    else RUN(run_g2_clear(st, n, pts, out, true, redo));
+    RUN(run_hash_g1_g2(st, n, g1, msgs, off, out, redo));
+    return 0;
+}
+// sign = sk * hash_g2(msg): the hash through the two-kernel path into scratch, then the multiplication kernel (h == nullptr); sign_g2
+// takes the caller's points
+static int impl_sign(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
+    if (!n) return 0;
+    if (!h && ctx->hash_algo != 1) {
+        u8 *hs = (u8 *)arena_alloc(ctx, d, n * 192);
+        if (!hs || impl_hash_g2(ctx, d, st, n, msgs, off, hs)) return -1;
+        h = hs;
+    }
+    RUN(run_sign(st, n, sk, msgs, off, h, out));
     return 0;
 }
 // ---- sum_s k_s P_s per item as a multi-scalar multiplication (scheme.cuh, *_msm_*).
@@ -433,7 +454,7 @@ extern "C" int tcb_verify_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const 
 }
 extern "C" int tcb_sign_batch_dev(tcb_ctx *ctx, void *stream, size_t n, const u8 *sk, const u8 *msgs, const u64 *off, const u8 *h, u8 *out) {
     DEV_PROLOGUE
-    DEV_RETURN(impl_sign(ctx, st, n, sk, msgs, off, h, out));
+    DEV_RETURN(impl_sign(ctx, d, st, n, sk, msgs, off, h, out));
 }
 extern "C" int tcb_combine_g2_batch_dev(tcb_ctx *ctx, void *stream, size_t n, size_t t, const u8 *x, const u8 *shares, u8 *out, u8 *status) {
     DEV_PROLOGUE
@@ -586,7 +607,7 @@ extern "C" int tcb_hash_g1_g2_batch(tcb_ctx *ctx, size_t n, const u8 *g1, const 
         u8 *dg = up(ctx, d, g1 + 96 * s.lo, 96 * cnt);
         u8 *dout = (u8 *)arena_alloc(ctx, d, 192 * cnt);
         if (!dg || !dout) return -1;
-        RUN(run_hash_g1_g2(st, cnt, dg, dm, doff, dout));
+        if (impl_hash_g1_g2(ctx, d, st, cnt, dg, dm, doff, dout)) return -1;
         if (down(ctx, d, out + 192 * s.lo, dout, 192 * cnt)) return -1;
     END_FOR_EACH_DEV
     return sync_all(ctx);
@@ -617,7 +638,7 @@ static int sign_common(tcb_ctx *ctx, size_t n, const u8 *sk, const u8 *msgs, con
         u8 *dsk = up(ctx, d, sk + 32 * s.lo, 32 * cnt);
         u8 *dout = (u8 *)arena_alloc(ctx, d, 192 * cnt);
         if (!dsk || !dout) return -1;
-        if (impl_sign(ctx, st, cnt, dsk, dm, doff, dh, dout)) return -1;
+        if (impl_sign(ctx, d, st, cnt, dsk, dm, doff, dh, dout)) return -1;
         if (down(ctx, d, out + 192 * s.lo, dout, 192 * cnt)) return -1;
         CK(cudaMemsetAsync(dsk, 0, 32 * cnt, st));   // wipe the secret scalars from scratch
     END_FOR_EACH_DEV
@@ -782,7 +803,7 @@ extern "C" int tcb_encrypt_batch(tcb_ctx *ctx, size_t n, const u8 *pk, const u8 
         u8 *dh = (u8 *)arena_alloc(ctx, d, 192 * cnt), *dw = (u8 *)arena_alloc(ctx, d, 192 * cnt);
         if (!dpk || !dr || !du || !dv || !dh || !dw) return -1;
         RUN(run_encrypt_uv(st, cnt, dpk, dr, dm, doff, du, dv));
-        RUN(run_hash_g1_g2(st, cnt, du, dv, doff, dh));
+        if (impl_hash_g1_g2(ctx, d, st, cnt, du, dv, doff, dh)) return -1;
         RUN(run_sign(st, cnt, dr, nullptr, nullptr, dh, dw));
         if (down(ctx, d, u_out + 96 * s.lo, du, 96 * cnt) || down(ctx, d, v_out + off[s.lo], dv, mbytes) ||
             down(ctx, d, w_out + 192 * s.lo, dw, 192 * cnt)) return -1;

@@ -293,7 +293,7 @@ TCB_HDN Fp fp_inv(const Fp &yin) {
 // Legendre symbol of a (any representative < p; Montgomery form is fine because R = (2^192)^2 is
 // a square): binary Jacobi algorithm, no multiplications.  Returns true iff a is a nonzero square
 // or zero (i.e. a has a square root in Fp).
-TCB_HDN bool fp_is_square(const Fp &y) {
+TCB_HDN bool fp_is_square_basic(const Fp &y) {      // one halving per iteration (reference version for the self-tests)
     u32 a[12], b[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) { a[i] = y.l[i]; b[i] = FpParams::mod(i); }
@@ -328,6 +328,58 @@ TCB_HDN bool fp_is_square(const Fp &y) {
         a[11] >>= 1;
     }
     // gcd is in b: b == 1 unless y == 0 (then b = p and the symbol is 0 -> has the root 0)
+    return neg == 0;
+}
+// Production version: the same binary Jacobi algorithm with ALL trailing zero bits of a removed per iteration (one funnel shift
+// per limb) and the swap as selects, so an iteration is one subtraction: ~0.7 * 381 iterations of ~80 instructions instead of
+// up to 762 of ~110.  Invariant: b odd, (y/p) = (-1)^neg * (a/b).
+TCB_HD u32 ctz32(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return (u32)(__ffs((int)v) - 1);
+#else
+    return (u32)__builtin_ctz(v);
+#endif
+}
+TCB_HDN bool fp_is_square(const Fp &y) {
+    u32 a[12], b[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { a[i] = y.l[i]; b[i] = FpParams::mod(i); }
+    u32 neg = 0;
+    for (int it = 0; it < 2 * 381 + 12; it++) {
+        u32 nz = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) nz |= a[i];
+        if (nz == 0) break;
+        // a <- a / 2^k, k = number of trailing zeros (at most 31 per iteration); (2/b) = -1 iff b = 3, 5 mod 8
+        u32 k = a[0] ? ctz32(a[0]) : 31u;
+        u32 b8 = b[0] & 7u;
+        neg ^= (k & 1u) & ((b8 == 3u || b8 == 5u) ? 1u : 0u);
+        if (k) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+            for (int i = 0; i < 11; i++) a[i] = __funnelshift_r(a[i], a[i + 1], k);
+#else
+#pragma unroll
+            for (int i = 0; i < 11; i++) a[i] = (a[i] >> k) | (a[i + 1] << (32 - k));
+#endif
+            a[11] >>= k;
+        }
+        if (!(a[0] & 1u)) continue;                        // the low limb was zero: more zeros to remove
+        // a odd: order the pair (reciprocity: a sign flip iff both = 3 mod 4), then a <- a - b (even again)
+        u32 t[12], bw;
+        sub_cc(t[0], a[0], b[0]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) subc_cc(t[i], a[i], b[i]);
+        subc(bw, 0, 0);                                    // all-ones if a < b
+        neg ^= ((a[0] & b[0]) >> 1) & 1u & bw;
+        // a < b: (a, b) <- (b - a, a) = (-t, a); else a <- t.  -t = (t ^ m) + (m & 1) with m = all-ones
+#pragma unroll
+        for (int i = 0; i < 12; i++) { b[i] = bw ? a[i] : b[i]; t[i] ^= bw; }
+        add_cc(a[0], t[0], bw & 1u);
+#pragma unroll
+        for (int i = 1; i < 11; i++) addc_cc(a[i], t[i], 0);
+        addc(a[11], t[11], 0);
+    }
     return neg == 0;
 }
 TCB_HD Fp fp_to_mont(const Fp &a) { return a * CONSTS().r2; }
