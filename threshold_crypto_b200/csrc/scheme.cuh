@@ -961,9 +961,10 @@ TCB_HD Jac<Fp> commit_eval_step(const Jac<Fp> &acc_in, const u32 *k, int top, co
     if (top < 0) acc = jac_inf<Fp>();
     else {
         Jac<Fp> base = acc;
+        Fp bz2 = sqr(base.z), bz3 = bz2 * base.z;       // shared by every "+ base" of this step
         for (int b = top - 1; b >= 0; b--) {
             acc = jac_dbl(acc);
-            if ((k[b >> 5] >> (b & 31)) & 1) acc = jac_add(acc, base);
+            if ((k[b >> 5] >> (b & 31)) & 1) acc = jac_add_cached(acc, base, bz2, bz3);
         }
     }
     return jac_add_mixed(acc, c);

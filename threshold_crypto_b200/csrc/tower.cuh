@@ -927,6 +927,29 @@ TCB_HDN Jac<F> jac_add(const Jac<F> &p, const Jac<F> &q) {   // add-2007-bl + ex
     r.z = (sqr(p.z + q.z) - z1z1 - z2z2) * h;
     return r;
 }
+// p + q with q's z^2 and z^3 supplied (a base that is added many times: Horner steps of Commitment::evaluate): 10M + 4S
+template <class F>
+TCB_HDN Jac<F> jac_add_cached(const Jac<F> &p, const Jac<F> &q, const F &z2z2, const F &z2c) {
+    if (jac_is_inf(p)) return q;
+    if (jac_is_inf(q)) return p;
+    F z1z1 = sqr(p.z);
+    F u1 = p.x * z2z2, u2 = q.x * z1z1;
+    F s1 = p.y * z2c, s2 = q.y * p.z * z1z1;
+    if (eq(u1, u2)) {
+        if (eq(s1, s2)) return jac_dbl(p);
+        return jac_inf<F>();
+    }
+    F h = u2 - u1;
+    F i = sqr(dbl(h));
+    F j = h * i;
+    F rr = dbl(s2 - s1);
+    F v = u1 * i;
+    Jac<F> r;
+    r.x = sqr(rr) - j - dbl(v);
+    r.y = rr * (v - r.x) - dbl(s1 * j);
+    r.z = (sqr(p.z + q.z) - z1z1 - z2z2) * h;
+    return r;
+}
 // k * P for an affine base, k given as NL little-endian u32 limbs (canonical integer).
 // MSB-first double-and-add; the group element is unique whatever the algorithm (App. A).
 template <class F, int NL>
