@@ -84,6 +84,56 @@ def test_threshold_enc_decrypt_roundtrip(tc, O):     # src/lib.rs:908-939 (encry
         pk_set.decrypt({8: shares[8], 5: shares[5]}, ct)
 
 
+def test_hash_g2(tc, O):                      # src/lib.rs:943-953, plus the bytes of the oracle (1000-byte messages: several SHA3 blocks)
+    r = rng()
+    msg = r.bytes(1000)
+    msgs = [msg, msg, msg + b"end0", msg + b"end1"]
+    h = tc.engine().hash_g2_batch(msgs)
+    assert np.array_equal(h[0], h[1])
+    assert not np.array_equal(h[0], h[2]) and not np.array_equal(h[2], h[3])
+    assert np.array_equal(h, O.hash_g2_batch(msgs))
+
+
+def test_hash_g1_g2(tc, O):                   # src/lib.rs:956-969 (messages longer than 64 bytes are hashed first)
+    r = rng()
+    msg = r.bytes(1000)
+    g0, g1 = tc.SecretKey(int.from_bytes(r.bytes(40), "little")).public_key().raw, tc.SecretKey(int.from_bytes(r.bytes(40), "little")).public_key().raw
+    pts = np.stack([g0, g0, g0, g0, g1])
+    msgs = [msg, msg, msg + b"end0", msg + b"end1", msg]
+    h = tc.engine().hash_g1_g2_batch(pts, msgs)
+    assert np.array_equal(h[0], h[1])
+    assert not np.array_equal(h[0], h[2]) and not np.array_equal(h[2], h[3]) and not np.array_equal(h[0], h[4])
+    for k in range(5):
+        assert np.array_equal(h[k], O.hash_g1_g2(pts[k], msgs[k]))
+
+
+def test_xor_with_hash(tc, O):                # src/lib.rs:972-982, through decrypt with t = 0 (the body is xored with the hash of the share)
+    r = rng()
+    g0, g1 = tc.SecretKey(int.from_bytes(r.bytes(40), "little")).public_key().raw, tc.SecretKey(int.from_bytes(r.bytes(40), "little")).public_key().raw
+    E = tc.engine()
+    x1 = tc._frs([1])
+
+    def xwh(g, body):
+        out, st = E.decrypt_batch(1, 0, x1, g, [body])
+        assert not st.any()
+        return out[0]
+    assert xwh(g0, bytes(5)) == xwh(g0, bytes(5)) and xwh(g0, bytes(5)) != xwh(g1, bytes(5))
+    for n in (5, 6, 20):
+        assert len(xwh(g0, bytes(n))) == n
+    assert xwh(g0, bytes(20)) == O.decrypt_batch(1, 0, x1, g0, [bytes(20)])[0][0]
+
+
+def test_random_extreme_thresholds(tc):       # src/lib.rs:900-905: threshold 0 — every share is the master key
+    sks = tc.SecretKeySet.random(0, rng())
+    assert sks.threshold() == 0
+    pks = sks.public_keys()
+    msg = b"one share suffices"
+    share = sks.secret_key_share(7).sign(msg)
+    assert pks.public_key_share(7).verify(share, msg)
+    assert pks.combine_signatures({7: share}) == sks.secret_key().sign(msg)
+    assert pks.public_key().verify(pks.combine_signatures({7: share}), msg)
+
+
 def test_poly_kat(tc):                        # src/poly.rs:783-797: 5 X^3 + X - 2
     poly = tc.Poly([-2, 1, 0, 5])
     for x, y in ((-1, -8), (2, 40), (3, 136), (5, 628)):
