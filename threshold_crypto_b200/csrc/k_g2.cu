@@ -4,6 +4,7 @@
 // k_hash_g2 runs 2x faster.  (The quad pairing kernel in k_pairing.cu prefers them inlined.)
 #define TCB_FP2S_NOINLINE 1
 #define TCB_FP_POW_CALL 1      // fixed-exponent powers (square roots) call one shared Fp multiply (tower.cuh)
+#define TCB_Q_CALLS 1          // cell products of g2sm.cuh as calls: inlined (the pairing kernels' policy, quadsm.cuh) k_g2_msm_acc_sm is slower (29.9 vs 27.7 ms per 2^14 combines)
 #include "kern.h"
 #include "scheme.cuh"
 #include "g2sm.cuh"

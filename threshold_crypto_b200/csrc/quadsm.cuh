@@ -24,6 +24,16 @@
 #include "scheme.cuh"
 
 #if defined(__CUDACC__)
+// The single Fp products of the cell engine (q_fmul, the product inside q_sqr) and the 2-term dot q_mul2 are INLINED at their call
+// sites: the by-value call ABI moved 24 + 12 registers per product and kept ptxas from scheduling the additions / selects of a step
+// between the multiplies.  Measured on one box (profiles/kbench_r2v*.json, r2w*): pairing check 61.3 ms with all three as calls,
+// 58.8 (q_sqr's product inline), 58.65 (+ q_fmul), 58.2 (+ q_mul2); unrolling the chunk loop of q_dot on top: 59.8 (255 registers
+// and spills in the Miller kernel).  -DTCB_Q_CALLS restores the calls.
+#if !defined(TCB_Q_CALLS)
+#define TCB_QSQR_INLINE 1
+#define TCB_QFMUL_INLINE 1
+#define TCB_QMUL2_INLINE 1
+#endif
 namespace tcb {
 
 constexpr int QNT = 128;                 // threads per block (32 quads)
@@ -89,7 +99,11 @@ TCB_D Fp q_dot(const u32 (*x)[12], const u32 *vre) {
     u32 even[12], odd[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) { even[i] = 0; odd[i] = 0; }
+#if defined(TCB_QDOT_UNROLL)
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int c = 0; c < 3; c++) {
         u32 y4[2 * T][4];
 #pragma unroll
@@ -116,9 +130,17 @@ TCB_D void stg_fp2(Fp *p, const Fp &v) {
     q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]); q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]); q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
 }
 // single Fp product as a call (by-value ABI: operands and result in registers) whatever the translation unit inlines elsewhere
+#if defined(TCB_QFMUL_INLINE)
+TCB_D Fp q_fmul(Fp a, Fp b) { return mmul<FpParams>(a, b); }
+#else
 static __device__ __noinline__ Fp q_fmul(Fp a, Fp b) { return mmul<FpParams>(a, b); }
+#endif
 // Fp2 product of two cell-resident values (my half)
+#if defined(TCB_QMUL2_INLINE)
+TCB_D Fp q_mul2(u32 ure, u32 vre) {
+#else
 static __device__ __noinline__ Fp q_mul2(u32 ure, u32 vre) {
+#endif
     u32 x[2][12];
     q_load_x<1>(x, &ure);
     return q_dot<1>(x, &vre);
@@ -145,7 +167,11 @@ TCB_D Fp q_sqr(u32 s) {
     bool e = q_role();
     Fp x = q_add_raw(own, fp_select(e, own, part));
     Fp y = fp_select(e, part, q_sub_raw(own, part));
+#if defined(TCB_QSQR_INLINE)
+    return mmul<FpParams>(x, y);      // experiment: let ptxas interleave the independent squares of a step (profiles/README.md)
+#else
     return q_fmul(x, y);
+#endif
 }
 // Three 3-term Fp2 dot products with the SAME left operands (u0, u1, u2):  r_d = sum_t U_t * V_{d,t}.  The results are written
 // to the slots d0..d2 (my column) after every lane of the warp has finished reading, so they may alias the operands.

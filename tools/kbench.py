@@ -24,6 +24,8 @@ if "HASH_ALGO" in os.environ:
     E.set_hash_algo(int(os.environ["HASH_ALGO"]))
 if "VERIFY_HASH" in os.environ:
     E.set_verify_hash(int(os.environ["VERIFY_HASH"]))
+if "MSM_ALGO" in os.environ:
+    E.set_msm_algo(int(os.environ["MSM_ALGO"]))
 dev = torch.device("cuda", 0)
 st = torch.cuda.current_stream().cuda_stream
 rng = np.random.default_rng(7)
