@@ -28,7 +28,8 @@
 // sites: the by-value call ABI moved 24 + 12 registers per product and kept ptxas from scheduling the additions / selects of a step
 // between the multiplies.  Measured on one box (profiles/kbench_r2v*.json, r2w*): pairing check 61.3 ms with all three as calls,
 // 58.8 (q_sqr's product inline), 58.65 (+ q_fmul), 58.2 (+ q_mul2); unrolling the chunk loop of q_dot on top: 59.8 (255 registers
-// and spills in the Miller kernel).  -DTCB_Q_CALLS restores the calls.
+// and spills in the Miller kernel); two q_mul2 of the doubling step jammed into one chunk loop: 58.1 vs 58.1 (no change, removed).
+// -DTCB_Q_CALLS restores the calls.
 #if !defined(TCB_Q_CALLS)
 #define TCB_QSQR_INLINE 1
 #define TCB_QFMUL_INLINE 1
