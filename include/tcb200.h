@@ -65,8 +65,10 @@ int tcb_set_msm_groups(tcb_ctx *ctx, size_t groups);
 /* Algorithm of that multi-scalar multiplication: 0 (default) Straus with shared doublings and mixed additions from
  * affine per-share tables, 1 batch-affine pairwise tree + Horner (28 % fewer multiplications, but slower on B200:
  * bound by global-memory latency at 2 warps per scheduler), 2 one scalar multiplication per share, 3 the G2 accumulation with one
- * item per thread, 4 the G2 accumulation on shared-memory cells at 4 blocks/SM (g2sm.cuh: faster below ~4 k items, slower at 2^14).
- * Same outputs; 1-4 exist for measurement. */
+ * item per thread, 4 the G2 accumulation on shared-memory cells at 4 blocks/SM (g2sm.cuh: faster below ~4 k items, slower at 2^14),
+ * 5 = 0 without the "spill" layout, 6 = 0 with the spill layout forced.  (Spill: when one unit per item leaves unit slots of the
+ * single wave idle — 2^14 items on 18 944 slots — the last share of every item moves to the spare units, a few items each, so the
+ * longest unit gets shorter; chosen automatically by 0.)  Same outputs; 1-6 exist for measurement and tests. */
 int tcb_set_msm_algo(tcb_ctx *ctx, int algo);
 /* Commitment::evaluate: units (coefficient blocks) per evaluation point.  0 (default) = chosen from the batch size (small batches
  * are split so that they fill the GPU), 1 = never split, k > 1 = force k.  Same outputs. */

@@ -98,6 +98,13 @@ static void g2_msm(size_t n, size_t m, const u32 *k, const u8 *pts, u8 *out, u8 
     std::vector<Gls4Digits> dg(n * m);
     std::vector<JacStore<Fp2>> part(n * G);
     for (size_t u = 0; u < n * m; u++) task_g2_msm_prep<Fp2>(u, k, pts, tab.data(), dg.data(), status, m);
+    if (g_algo == 6 && m >= 2) {            // spill layout (forced): main units + units that take the last share of q = 2 items
+        const size_t q = 2, units = n + (n + q - 1) / q;
+        part.assign(n * 2, JacStore<Fp2>());
+        for (size_t w = 0; w < units; w++) task_g2_msm_acc_spill<Fp2>(w, n, m, q, tab.data(), dg.data(), part.data());
+        for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, 2, part.data(), out);
+        return;
+    }
     if (g_algo == 1) msm_acc_ba<MsmG2<Fp2>>(n, m, G, tab.data(), dg.data(), part.data());
     else for (size_t w = 0; w < n * G; w++) task_g2_msm_acc<Fp2>(w, m, G, tab.data(), dg.data(), part.data());
     for (size_t i = 0; i < n; i++) task_g2_sum<Fp2>(i, G, part.data(), out);

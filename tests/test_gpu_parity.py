@@ -137,7 +137,7 @@ def test_msm_groupings_and_edges(gpu_engine, O):
     with the automatic choice: zero / one / r-1 scalars, infinity shares, repeated and cancelling pairs."""
     E = gpu_engine
     try:
-      for algo in (0, 1, 2, 3, 4):
+      for algo in (0, 1, 2, 3, 4, 5, 6):
         E.set_msm_algo(algo)
         for g in (1, 2, 3, 1000, 0):
             E.set_msm_groups(g)

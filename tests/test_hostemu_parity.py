@@ -38,7 +38,7 @@ def test_hostemu_golden(emu, golden):
 def test_hostemu_msm_groupings(emu, O):
     """Shared-doubling MSM with 1, 2 and m groups per item (m groups = one share per unit)."""
     try:
-        for algo in (0, 1):          # Straus with mixed additions, batch-affine tree
+        for algo in (0, 1, 6):       # Straus with mixed additions, batch-affine tree, Straus in the spill layout
             emu.set_msm_algo(algo)
             for g in (1, 2, 64):
                 emu.set_msm_groups(g)

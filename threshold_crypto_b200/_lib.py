@@ -104,7 +104,7 @@ class Engine:
 
     def set_msm_algo(self, algo):
         """0 Straus / shared doublings (default), 1 batch-affine tree, 2 one multiplication per share, 3 G2 accumulation per thread,
-        4 G2 accumulation on shared-memory cells."""
+        4 G2 accumulation on shared-memory cells, 5 Straus without the spill layout, 6 Straus with the spill layout forced."""
         self._ck(self.lib.tcb_set_msm_algo(self.ctx, int(algo)))
 
     def set_eval_split(self, units):

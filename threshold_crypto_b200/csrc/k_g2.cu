@@ -50,6 +50,11 @@ __global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_acc(size_t units, s
     size_t i = unit_index();
     if (i < units) task_g2_msm_acc<F2>(i, m, G, tab, dg, out);
 }
+// spill layout (scheme.cuh: task_g2_msm_acc_spill): n main units + ceil(n / q) units that take the last share of q items each
+__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_msm_acc_spill(size_t units, size_t n, size_t m, size_t q, const AffStore<F2> *tab, const Gls4Digits *dg, JacStore<F2> *out) {
+    size_t i = unit_index();
+    if (i < units) task_g2_msm_acc_spill<F2>(i, n, m, q, tab, dg, out);
+}
 // the same accumulation with the running point, the table entry and the temporaries in shared-memory cells (g2sm.cuh): 4 blocks/SM
 #ifndef TCB_G2SM_MINB
 #define TCB_G2SM_MINB 4
@@ -95,6 +100,10 @@ void run_g2_decompress(cudaStream_t st, size_t n, const u8 *in, u8 *out, u8 *sta
 size_t g2_term_bytes() { return sizeof(JacStore<F2>); }
 void run_g2_mul_store(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *terms, u8 *status, size_t per_item) {
     if (units) k_g2_mul_store<<<grid2(units), 128, 0, st>>>(units, k, pts, (JacStore<F2> *)terms, status, per_item);
+}
+void run_g2_msm_acc_spill(cudaStream_t st, size_t n, size_t m, size_t q, const void *tab, const void *dg, void *out) {
+    size_t units = n + (n + q - 1) / q;
+    if (n) k_g2_msm_acc_spill<<<grid2(units), 128, 0, st>>>(units, n, m, q, (const AffStore<F2> *)tab, (const Gls4Digits *)dg, (JacStore<F2> *)out);
 }
 size_t g2_msm_tab_bytes() { return 8 * sizeof(AffStore<F2>); }
 size_t g2_msm_dg_bytes() { return sizeof(Gls4Digits); }

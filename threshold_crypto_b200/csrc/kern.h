@@ -42,6 +42,7 @@ size_t g2_msm_dg_bytes();        // per (item, share): recoded scalar
 size_t g2_msm_units_per_sm();    // resident (item, group) units per SM of k_g2_msm_acc
 void run_g2_msm_prep(cudaStream_t st, size_t units, const u32 *k, const u8 *pts, void *tab, void *dg, u8 *status, size_t per_item);
 void run_g2_msm_acc(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out);
+void run_g2_msm_acc_spill(cudaStream_t st, size_t n, size_t m, size_t q, const void *tab, const void *dg, void *out);   // 2 partial sums per item
 size_t g2_msm_sm_units_per_sm();  // the accumulation on shared-memory cells (g2sm.cuh): 4 blocks/SM
 void run_g2_msm_acc_sm(cudaStream_t st, size_t units, size_t m, size_t G, const void *tab, const void *dg, void *out);
 // batch-affine accumulation: scratch per unit = 2 point buffers + prefix products for up to cnt_max shares per unit

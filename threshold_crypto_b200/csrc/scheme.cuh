@@ -659,11 +659,9 @@ TCB_HD Aff<F2> g2_msm_fetch(const AffStore<F2> *tab, const Gls4Digits *dgs, size
     if (d & 1) t.y = -t.y;
     return t;
 }
+// sum of the shares base, base + G, ..., base + (cnt - 1) G (units of the prep arrays) with shared doublings
 template <class F2>
-TCB_HD void task_g2_msm_acc(size_t w, size_t m, size_t G, const AffStore<F2> *tab, const Gls4Digits *dgs, JacStore<F2> *out) {
-    size_t item = w / G, g = w % G;
-    size_t cnt = (m - g + G - 1) / G;          // shares g, g + G, ... of this item (g < G <= m)
-    size_t base = item * m + g;
+TCB_HD Jac<F2> g2_msm_walk(size_t base, size_t G, size_t cnt, const AffStore<F2> *tab, const Gls4Digits *dgs) {
     Jac<F2> acc = jac_inf<F2>();
     // flattened (digit, share) sequence with the next table entry fetched before the current addition
     Aff<F2> nxt = g2_msm_fetch<F2>(tab, dgs, base, GLS4_L);
@@ -689,7 +687,31 @@ TCB_HD void task_g2_msm_acc(size_t w, size_t m, size_t G, const AffStore<F2> *ta
         t.x = F2::load(tab[8 * u].x); t.y = -F2::load(tab[8 * u].y); t.inf = false;
         acc = jac_add_mixed(acc, t);
     }
+    return acc;
+}
+template <class F2>
+TCB_HD void task_g2_msm_acc(size_t w, size_t m, size_t G, const AffStore<F2> *tab, const Gls4Digits *dgs, JacStore<F2> *out) {
+    size_t item = w / G, g = w % G;
+    size_t cnt = (m - g + G - 1) / G;          // shares g, g + G, ... of this item (g < G <= m)
+    Jac<F2> acc = g2_msm_walk<F2>(item * m + g, G, cnt, tab, dgs);
     acc.x.store(out[w].x); acc.y.store(out[w].y); acc.z.store(out[w].z);
+}
+// "Spill" layout for batches that leave part of the GPU's resident units idle with one unit per item (2^14 items on 18 944 unit
+// slots): unit w < n adds the first m - 1 shares of item w, the spare units each add the LAST share of q items, one after the other,
+// so that every unit walks less than the one-unit-per-item plan and all slots are used.  Two partial sums per item: out[2 item],
+// out[2 item + 1] (then task_g2_sum with two terms).
+template <class F2>
+TCB_HD void task_g2_msm_acc_spill(size_t w, size_t n, size_t m, size_t q, const AffStore<F2> *tab, const Gls4Digits *dgs, JacStore<F2> *out) {
+    if (w < n) {
+        Jac<F2> acc = g2_msm_walk<F2>(w * m, 1, m - 1, tab, dgs);
+        acc.x.store(out[2 * w].x); acc.y.store(out[2 * w].y); acc.z.store(out[2 * w].z);
+        return;
+    }
+    size_t lo = (w - n) * q, hi = lo + q < n ? lo + q : n;
+    for (size_t item = lo; item < hi; item++) {
+        Jac<F2> acc = g2_msm_walk<F2>(item * m + m - 1, 1, 1, tab, dgs);
+        acc.x.store(out[2 * item + 1].x); acc.y.store(out[2 * item + 1].y); acc.z.store(out[2 * item + 1].z);
+    }
 }
 
 // t == 0 shortcut of interpolate (src/lib.rs:735-737): the first sample is returned unchanged

@@ -185,7 +185,7 @@ static size_t pick_groups(size_t n, size_t m, size_t units_per_wave, double fixe
     }
     return best;
 }
-enum { MSM_STRAUS = 0, MSM_BATCH_AFFINE = 1, MSM_PER_SHARE = 2, MSM_STRAUS_G2_THREAD = 3, MSM_STRAUS_G2_CELLS = 4 };
+enum { MSM_STRAUS = 0, MSM_BATCH_AFFINE = 1, MSM_PER_SHARE = 2, MSM_STRAUS_G2_THREAD = 3, MSM_STRAUS_G2_CELLS = 4, MSM_STRAUS_NO_SPILL = 5, MSM_STRAUS_FORCE_SPILL = 6 };
 // out: G Jacobian partial sums per item in `part` (then run_g*_sum(n, G, part, ...))
 static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
     const size_t term = g2 ? g2_term_bytes() : g1_term_bytes();
@@ -198,6 +198,7 @@ static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t 
         return 0;
     }
     const bool ba = ctx->msm_algo == MSM_BATCH_AFFINE;
+    const bool plain_straus = ctx->msm_algo == MSM_STRAUS || ctx->msm_algo == MSM_STRAUS_NO_SPILL || ctx->msm_algo == MSM_STRAUS_FORCE_SPILL;
     const bool g2_thread = g2 && ctx->msm_algo == MSM_STRAUS_G2_THREAD;
     // the G2 accumulation on shared-memory cells (g2sm.cuh, 4 blocks/SM): measured 23.0 vs 19.3 ms at 2^14 items (G = 2 costs 17 % more
     // multiply-accumulates and the multiply pipe is the limit either way), 4.2 vs 4.6 ms at 2048 items — a measurement knob, not the default
@@ -210,6 +211,19 @@ static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t 
     double fixed = g2 ? (ba ? 4.8 + 8.6 + 6.0 : 4.8) : (ba ? 14.0 + 11.0 + 6.0 : 14.0);
     double share = g2 ? (ba ? 5.2 : 8.6) : (ba ? 5.7 : 11.0);
     G = ctx->msm_groups ? (ctx->msm_groups < m ? ctx->msm_groups : m) : pick_groups(n, m, ps * (size_t)ctx->sm_count, fixed, share);
+    // G2, one unit per item, and the batch leaves unit slots of the single wave idle (2^14 items on 18 944 slots): move the last share of
+    // every item to the spare units, q items each (scheme.cuh: task_g2_msm_acc_spill) — when that shortens the longest unit
+    size_t spill_q = 0;
+    if (g2 && ctx->msm_algo == MSM_STRAUS_FORCE_SPILL && m >= 2) { G = 1; spill_q = 2; }       // tests: the layout on any batch
+    if (g2 && ctx->msm_algo == MSM_STRAUS && G == 1 && m >= 3 && !ctx->msm_groups) {
+        const size_t wave = ps * (size_t)ctx->sm_count;
+        if (n < wave && n >= wave / 2) {
+            size_t q = (n + (wave - n) - 1) / (wave - n);
+            double now = fixed + share * (double)m, main_u = fixed + share * (double)(m - 1), coll = (double)q * (fixed + share);
+            if ((main_u > coll ? main_u : coll) < 0.97 * now) spill_q = q;
+        }
+    }
+    if (spill_q) G = 2;
     void *tab = arena_alloc(ctx, d, n * m * (g2 ? g2_msm_tab_bytes() : g1_msm_tab_bytes()));
     void *dg = arena_alloc(ctx, d, n * m * (g2 ? g2_msm_dg_bytes() : g1_msm_dg_bytes()));
     part = arena_alloc(ctx, d, n * G * term);
@@ -219,6 +233,7 @@ static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t 
     if (!ba) {
         if (g2_thread) RUN(run_g2_msm_acc_thread(st, n * G, m, G, tab, dg, part));
         else if (g2_cells) RUN(run_g2_msm_acc_sm(st, n * G, m, G, tab, dg, part));
+        else if (g2 && spill_q) RUN(run_g2_msm_acc_spill(st, n, m, spill_q, tab, dg, part));
         else if (g2) RUN(run_g2_msm_acc(st, n * G, m, G, tab, dg, part));
         else RUN(run_g1_msm_acc(st, n * G, m, G, tab, dg, part));
         return 0;
@@ -386,7 +401,7 @@ extern "C" int tcb_set_eval_split(tcb_ctx *ctx, size_t units) {
     return 0;
 }
 extern "C" int tcb_set_msm_algo(tcb_ctx *ctx, int algo) {
-    if (!ctx || algo < 0 || algo > 4) return -2;
+    if (!ctx || algo < 0 || algo > 6) return -2;
     ctx->msm_algo = algo;
     return 0;
 }
