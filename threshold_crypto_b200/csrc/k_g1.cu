@@ -38,7 +38,12 @@ __global__ void __launch_bounds__(128) k_g1_msm_prep(size_t units, const u32 *k,
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < units) task_g1_msm_prep(i, k, pts, tab, dg, status, per_item);
 }
-__global__ void __launch_bounds__(128) k_g1_msm_acc(size_t units, size_t m, size_t G, const Aff1Store *tab, const Glv2Digits *dg, Jac1Store *out) {
+// pinned to 3 blocks/SM (168 registers, no spills): left to ptxas the kernel drifted to 180 registers = 2 blocks/SM when unrelated code of
+// this translation unit changed (11.36 -> 11.75 ms per 2^12 x 65 shares, profiles/r2t_ vs r2z_other_kernels_raw_subset.json)
+#ifndef TCB_G1_MSM_MINB
+#define TCB_G1_MSM_MINB 3
+#endif
+__global__ void __launch_bounds__(128, TCB_G1_MSM_MINB) k_g1_msm_acc(size_t units, size_t m, size_t G, const Aff1Store *tab, const Glv2Digits *dg, Jac1Store *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < units) task_g1_msm_acc(i, m, G, tab, dg, out);
 }

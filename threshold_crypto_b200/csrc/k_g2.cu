@@ -20,7 +20,13 @@ __global__ void __launch_bounds__(128, TCB_G2_MINB) k_hash_g2(size_t n, const u8
     if (i < n) task_hash_g2<F2>(i, msgs, off, out, exact != 0, only);
 }
 // second half of the two-kernel hash_g2 (scheme.cuh: g2_random_point / task_g2_clear): cofactor clearing of the curve points
-__global__ void __launch_bounds__(128, TCB_G2_MINB) k_g2_clear(size_t n, const G2PointStore *pts, u8 *out, int exact, u8 *redo) {
+// The clearing kernel alone needs few registers (its Fp2 products are by-value calls): 128 registers = 4 blocks/SM without spills.
+// Measured on one box (profiles/kbench_r2g2*.json): exact hash_g2 19.47 ms at 2 blocks/SM, 18.76 at 3, 18.73 at 4; the other lane-pair
+// kernels stay at 2 blocks/SM (all of them at 3: combine 29.3 instead of 23.1 ms per 2^14, but 5.2 instead of 5.9 ms per 2048).
+#ifndef TCB_CLEAR_MINB
+#define TCB_CLEAR_MINB 4
+#endif
+__global__ void __launch_bounds__(128, TCB_CLEAR_MINB) k_g2_clear(size_t n, const G2PointStore *pts, u8 *out, int exact, u8 *redo) {
     size_t i = unit_index();
     if (i < n) task_g2_clear<F2>(i, pts, out, exact != 0, redo);
 }

@@ -1,0 +1,5 @@
+# A/B of experiment builds of the G2 lane-pair kernels: bash tools/experiments/ab_g2.sh "_c3 _c4 _g3"
+for v in "" $1; do
+  L=threshold_crypto_b200/csrc/libtcb200$v.so
+  TCB200_LIB=$L python tools/kbench.py r2g2$v verify,combine,sign 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['lib'], {k:round(v['best_ms'],2) for k,v in d.items() if isinstance(v,dict)})"
+done
