@@ -253,7 +253,9 @@ static __device__ __noinline__ void qf_exp_by_x(u64 x) {
 TCB_D void qf_put(u32 v, const Fp12Q &a) { __syncwarp(); qf_st12(v, a); __syncwarp(); }
 // same chain as quad.cuh final_exponentiation; the running value is V0, the second operand of every product goes through V1;
 // the other live values (r, y0..y3) wait in the local frame as own halves
-static __device__ __noinline__ bool qf_final_exp_is_one(const Fp12Q &in, Fp12Q &out) {
+// want_value == false: only the boolean is needed — the last product frob(y3) * y1 == 1 is tested as frob(y3) == conj(y1) (both factors are
+// in the cyclotomic subgroup, where the inverse is the conjugate) and `out` is left unset
+static __device__ __noinline__ bool qf_final_exp_is_one(const Fp12Q &in, Fp12Q &out, bool want_value) {
     const u64 x = TCB_BLS_X;
     // easy part: r = (conj(in) * in^-1)^(p^2 + 1)
     qf_put(QF_V0, in);
@@ -301,10 +303,15 @@ static __device__ __noinline__ bool qf_final_exp_is_one(const Fp12Q &in, Fp12Q &
     y1 = qf_ld12(QF_V0);
     qf_put(QF_V0, y3);
     qf_frob(QF_V0, 1);
+    bool p0 = q_pair() == 0, e = q_role();
+    if (!want_value) {
+        Fp12Q f3 = qf_ld12(QF_V0);
+        Fp12Q c1 = fp12_conj(y1);
+        return q_quad_and(f3.h.c0.h == c1.h.c0.h && f3.h.c1.h == c1.h.c1.h && f3.h.c2.h == c1.h.c2.h);
+    }
     qf_put(QF_V1, y1);
     qf_mul12(QF_V0, QF_V0, QF_V1);
     out = qf_ld12(QF_V0);
-    bool p0 = q_pair() == 0, e = q_role();
     Fp want = (p0 && !e) ? fp_one() : Fp::zero();
     return q_quad_and(out.h.c0.h == want && out.h.c1.h.is_zero() && out.h.c2.h.is_zero());
 }
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(QNT, TCB_FESM_MINB) k_final_exp_sm(size_t n, c
     Fp12Q f;
     f.h.c0.h = ldg_fp(p); f.h.c1.h = ldg_fp(p + 1); f.h.c2.h = ldg_fp(p + 2);
     Fp12Q g;
-    bool res = qf_final_exp_is_one(fp12_conj(f), g);
+    bool res = qf_final_exp_is_one(fp12_conj(f), g, fe_out != nullptr);
     if (live && fe_out) { Fp *o = fe_out + (i * 4 + (threadIdx.x & 3u)) * 3; stg_fp(o, g.h.c0.h); stg_fp(o + 1, g.h.c1.h); stg_fp(o + 2, g.h.c2.h); }
     if (live && (threadIdx.x & 3) == 0) ok[i] = (res && enc_ok[i]) ? 1 : 0;
 }
