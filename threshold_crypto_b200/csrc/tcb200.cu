@@ -328,7 +328,7 @@ extern "C" int tcb_init(tcb_ctx **out, const int *device_ids, int n_devices) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return -3;   // no CPU fallback
     tcb_ctx *ctx = new tcb_ctx();
-    { const char *e = getenv("TCB200_MSM_ALGO"); if (e && e[0] >= '0' && e[0] <= '4') ctx->msm_algo = e[0] - '0'; }
+    { const char *e = getenv("TCB200_MSM_ALGO"); if (e && e[0] >= '0' && e[0] <= '6') ctx->msm_algo = e[0] - '0'; }
     Consts C;
     build_consts(C);
     if (n_devices <= 0 || !device_ids) {
