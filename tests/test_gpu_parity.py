@@ -286,6 +286,39 @@ def test_hash_g2_algorithms_and_verify_modes(gpu_engine, O):
         O.set_threads(1)
 
 
+def test_verifier_pieces_compose_to_verify(gpu_engine, O):
+    """include/tcb200.h: tcb_verify_batch == tcb_verify_g2_batch(pk, tcb_verifier_hash_g2 points, tcb_verifier_generator, sig) in both
+    tcb_set_verify_hash modes; in the default mode the points are [3(x^2-1)] hash_g2(msg) (checked through the oracle's G2
+    multiplication), in mode 1 the oracle's hash_g2 itself."""
+    import torch
+    from threshold_crypto_b200._lib import pack_msgs
+    E = gpu_engine
+    n = 37
+    sk, pk, sig, msgs = cases.make_sig_batch(O, n, 94, corrupt_every=4)
+    exp = O.verify_batch(pk, sig, msgs)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    buf, off = pack_msgs(msgs)
+    d_msg, d_off = torch.from_numpy(buf).to(dev), torch.from_numpy(off.view(np.int64)).to(dev)
+    d_h = torch.zeros(n * 192, dtype=torch.uint8, device=dev)
+    c = 3 * (0xd201000000010000 ** 2 - 1)
+    try:
+        for mode in (0, 1):
+            E.set_verify_hash(mode)
+            E.dev_call("tcb_verifier_hash_g2_batch_dev", st, ("size", n), d_msg.data_ptr(), d_off.data_ptr(), d_h.data_ptr())
+            torch.cuda.synchronize()
+            h = d_h.cpu().numpy().reshape(n, 192)
+            want = O.hash_g2_batch(msgs)
+            if mode == 0:
+                want = O.sign_g2_batch(np.tile(fr_bytes([c]), n), want)          # [c] H(m)
+            assert np.array_equal(h, want), mode
+            gen = np.tile(E.verifier_generator(), (n, 1))
+            assert np.array_equal(E.verify_g2_batch(pk, h, gen, sig), exp), mode
+            assert np.array_equal(E.verify_batch(pk, sig, msgs), exp), mode
+    finally:
+        E.set_verify_hash(0)
+
+
 def _poly_shares(coeff_bytes, xs_ints):
     """host big-int Horner: f(x) for every x (canonical 32-byte little-endian scalars)"""
     from conftest import R
