@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../include/tcb200.h"
 #include "../../threshold_crypto_b200/csrc/scheme.cuh"
+#include "../../threshold_crypto_b200/csrc/msm_plan.h"
 using namespace tcb;
 
 struct tcb_ctx { int dummy; };
@@ -83,6 +84,13 @@ extern "C" void tcb_emu_set_groups(size_t g) { g_groups = g ? g : 1; }
 extern "C" int tcb_set_msm_groups(tcb_ctx *, size_t g) { g_groups = g ? g : 2; return 0; }
 static int g_algo = 0;
 extern "C" int tcb_set_msm_algo(tcb_ctx *, int a) { g_algo = a; return 0; }
+// the planning functions tcb200.cu uses (msm_plan.h): groups per item and the spill factor for a batch shape
+extern "C" void tcb_emu_msm_plan(size_t n, size_t m, size_t units_per_wave, int g2, size_t *G, size_t *q) {
+    double fixed, share;
+    tcbk::straus_costs(g2 != 0, fixed, share);
+    *G = tcbk::pick_groups(n, m, units_per_wave, fixed, share);
+    *q = (g2 && *G == 1) ? tcbk::pick_spill(n, m, units_per_wave, fixed, share) : 0;
+}
 static size_t g_eval_split = 0;
 extern "C" int tcb_set_eval_split(tcb_ctx *, size_t u) { g_eval_split = u > 1 ? u : 0; return 0; }
 template <class M, class JS>

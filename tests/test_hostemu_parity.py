@@ -51,6 +51,32 @@ def test_hostemu_msm_groupings(emu, O):
         emu.set_msm_algo(0)
 
 
+def test_msm_plan_for_the_baseline_shapes(emu):
+    """Host-side planning of the multi-scalar multiplication (csrc/msm_plan.h, the code tcb200.cu runs): groups per item and the
+    spill factor for the BASELINE shapes on a B200 (148 SMs; G2 accumulation 2 blocks x 64 lane pairs per SM, G1 3 blocks x 128
+    threads): config #3 (2^14 items, 11 shares) runs one unit per item with the last share spilled to the spare units, 7 items
+    each; one eighth of it (what a GPU gets in the 8-way sharded record) is split into 6 partial sums; config #4 (2^12 items,
+    65 shares) into 13."""
+    import ctypes as C
+    lib = emu.lib
+
+    def plan(n, m, wave, g2):
+        G, q = C.c_size_t(0), C.c_size_t(0)
+        lib.tcb_emu_msm_plan(C.c_size_t(n), C.c_size_t(m), C.c_size_t(wave), int(g2), C.byref(G), C.byref(q))
+        return G.value, q.value
+    w2, w1 = 2 * 64 * 148, 3 * 128 * 148
+    assert plan(1 << 14, 11, w2, True) == (1, 7)
+    assert plan(2048, 11, w2, True) == (6, 0)
+    assert plan(w2, 11, w2, True) == (1, 0)                  # a full wave: nothing to spill to
+    assert plan(9000, 11, w2, True) == (2, 0)                # two units per item still fit one wave
+    assert plan(1 << 12, 65, w1, False) == (13, 0)
+    assert plan(1 << 14, 2, w2, True)[1] == 0                # too few shares for the layout to pay
+    for n in (1, 100, 5000, 1 << 14, 1 << 18):
+        for m in (1, 2, 11, 65):
+            G, q = plan(n, m, w2, True)
+            assert 1 <= G <= m and (q == 0 or (G == 1 and n + (n + q - 1) // q <= w2))
+
+
 def test_binary_gcd_inverse_and_legendre_symbol(emu):
     """fp_inv (branch-free binary GCD) == Fermat inverse, fp_is_square (binary Jacobi) == Euler
     criterion, on random elements, every bit length, +-2^k and the edge values 0, 1, p-1 (host instantiation of tower.cuh);

@@ -26,6 +26,7 @@
 #include "../../include/tcb200.h"
 #include "kern.h"
 #include "scheme.cuh"
+#include "msm_plan.h"
 
 using namespace tcb;
 using namespace tcbk;
@@ -173,18 +174,7 @@ static int impl_sign(tcb_ctx *ctx, DevState &d, cudaStream_t st, size_t n, const
 // ---- sum_s k_s P_s per item as a multi-scalar multiplication (scheme.cuh, *_msm_*).
 // G partial sums ("groups") per item trade shared work (small G) against parallelism (large G); pick the G
 // that minimises  waves(n G) * (fixed + per_share * ceil(m / G)).
-static size_t pick_groups(size_t n, size_t m, size_t units_per_wave, double fixed_cost, double share_cost) {
-    size_t best = 1;
-    double best_cost = 1e300;
-    for (size_t G = 1; G <= m; G++) {
-        size_t per = (m + G - 1) / G;
-        if (G > 1 && (m + G - 2) / (G - 1) == per) continue;          // same depth as G - 1 with more units
-        double waves = (double)((n * G + units_per_wave - 1) / units_per_wave);
-        double cost = waves * (fixed_cost + share_cost * (double)per);
-        if (cost < best_cost * 0.999) { best_cost = cost; best = G; }
-    }
-    return best;
-}
+// (the planning functions live in msm_plan.h so that the host emulation's tests can pin their choices)
 enum { MSM_STRAUS = 0, MSM_BATCH_AFFINE = 1, MSM_PER_SHARE = 2, MSM_STRAUS_G2_THREAD = 3, MSM_STRAUS_G2_CELLS = 4, MSM_STRAUS_NO_SPILL = 5, MSM_STRAUS_FORCE_SPILL = 6 };
 // out: G Jacobian partial sums per item in `part` (then run_g*_sum(n, G, part, ...))
 static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t n, size_t m, const u32 *k, const u8 *pts, u8 *status, void *&part, size_t &G) {
@@ -215,14 +205,7 @@ static int impl_msm(tcb_ctx *ctx, DevState &d, cudaStream_t st, bool g2, size_t 
     // every item to the spare units, q items each (scheme.cuh: task_g2_msm_acc_spill) — when that shortens the longest unit
     size_t spill_q = 0;
     if (g2 && ctx->msm_algo == MSM_STRAUS_FORCE_SPILL && m >= 2) { G = 1; spill_q = 2; }       // tests: the layout on any batch
-    if (g2 && ctx->msm_algo == MSM_STRAUS && G == 1 && m >= 3 && !ctx->msm_groups) {
-        const size_t wave = ps * (size_t)ctx->sm_count;
-        if (n < wave && n >= wave / 2) {
-            size_t q = (n + (wave - n) - 1) / (wave - n);
-            double now = fixed + share * (double)m, main_u = fixed + share * (double)(m - 1), coll = (double)q * (fixed + share);
-            if ((main_u > coll ? main_u : coll) < 0.97 * now) spill_q = q;
-        }
-    }
+    if (g2 && ctx->msm_algo == MSM_STRAUS && G == 1 && !ctx->msm_groups) spill_q = pick_spill(n, m, ps * (size_t)ctx->sm_count, fixed, share);
     if (spill_q) G = 2;
     void *tab = arena_alloc(ctx, d, n * m * (g2 ? g2_msm_tab_bytes() : g1_msm_tab_bytes()));
     void *dg = arena_alloc(ctx, d, n * m * (g2 ? g2_msm_dg_bytes() : g1_msm_dg_bytes()));
